@@ -1,0 +1,12 @@
+"""diffphycon_b200 — B200-native (sm_100a) guided-diffusion sampling engine behind DiffPhyCon's Python API.
+
+Public surface (mirrors the reference modules named in SURVEY.md section 8(b)):
+    Unet3D_with_Conv3D          model/video_diffusion_pytorch/video_diffusion_pytorch_conv3d.py:356
+    GaussianDiffusion           diffusion/diffusion_2d_smoke.py:451
+    StockSmokeGuidance          inference/inference_2d_smoke.py:30-44 (closed-form, fused into the step kernel)
+The arithmetic lives in libdpc_b200.so (include/dpc_b200.h); there is no CPU or PyTorch fallback.
+"""
+from .diffusion_2d_smoke import SMOKE_RESCALER, GaussianDiffusion, StockSmokeGuidance  # noqa: F401
+from .unet3d import Unet3D_with_Conv3D  # noqa: F401
+
+__all__ = ["Unet3D_with_Conv3D", "GaussianDiffusion", "StockSmokeGuidance", "SMOKE_RESCALER"]

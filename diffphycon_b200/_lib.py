@@ -1,0 +1,194 @@
+"""ctypes binding of libdpc_b200.so (the C-ABI declared in include/dpc_b200.h).
+
+There is NO fallback: if the shared library is missing, or a kernel launch fails, this module raises.  PyTorch is
+used only for device memory and streams; every function here takes torch CUDA tensors and passes raw pointers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libdpc_b200.so")
+ABI_VERSION = 1
+
+c_fp = C.c_void_p
+
+
+class ConvParams(C.Structure):
+    """struct dpc_conv_params (include/dpc_b200.h)."""
+    _fields_ = [
+        ("x1", c_fp), ("x2", c_fp), ("w", c_fp), ("bias", c_fp), ("residual", c_fp), ("taps", c_fp), ("y", c_fp),
+        ("gn_stats", c_fp),
+        ("C1", C.c_int32), ("C2", C.c_int32),
+        ("B", C.c_int32), ("Fi", C.c_int32), ("Hi", C.c_int32), ("Wi", C.c_int32),
+        ("Fo", C.c_int32), ("Ho", C.c_int32), ("Wo", C.c_int32),
+        ("ntaps", C.c_int32),
+        ("st", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
+        ("pt", C.c_int32), ("ph", C.c_int32), ("pw", C.c_int32),
+        ("Cout", C.c_int32), ("Npad", C.c_int32), ("Kpad", C.c_int32),
+        ("Hfull", C.c_int32), ("Wfull", C.c_int32), ("oh_mul", C.c_int32), ("oh_off", C.c_int32),
+        ("ow_mul", C.c_int32), ("ow_off", C.c_int32),
+        ("out_layout", C.c_int32), ("gn_groups", C.c_int32), ("precise", C.c_int32),
+    ]
+
+
+class StepCoefs(C.Structure):
+    """struct dpc_step_coefs (include/dpc_b200.h)."""
+    _fields_ = [
+        ("sqrt_recip_alphas_cumprod", C.c_float), ("sqrt_recipm1_alphas_cumprod", C.c_float),
+        ("guidance_coef", C.c_float), ("prior_coef", C.c_float), ("w_energy", C.c_float),
+        ("rescaler", C.c_float * 6),
+        ("posterior_mean_coef1", C.c_float), ("posterior_mean_coef2", C.c_float), ("sigma", C.c_float),
+        ("add_noise", C.c_int32),
+        ("sqrt_alpha_next", C.c_float), ("c", C.c_float), ("ddim_sigma", C.c_float),
+        ("last", C.c_int32),
+    ]
+
+
+_lib = None
+
+_SIGNATURES = {
+    "dpc_abi_version": ([], C.c_int),
+    "dpc_last_error": ([], C.c_char_p),
+    "dpc_device_is_sm100": ([], C.c_int),
+    "dpc_conv_igemm": ([C.POINTER(ConvParams), c_fp], C.c_int),
+    "dpc_conv3d_tcgen05": ([C.POINTER(ConvParams), c_fp], C.c_int),
+    "dpc_groupnorm_silu": ([c_fp, c_fp, c_fp, c_fp, c_fp, C.c_int64, C.c_int64, c_fp, c_fp, C.c_int32, C.c_int64,
+                            C.c_int32, C.c_int32, C.c_float, c_fp], C.c_int),
+    "dpc_layernorm_channels": ([c_fp, c_fp, c_fp, C.c_int64, C.c_int32, C.c_float, c_fp], C.c_int),
+    "dpc_pack_input": ([c_fp, c_fp] + [C.c_int32] * 8 + [c_fp], C.c_int),
+    "dpc_temporal_attention": ([c_fp] * 5 + [C.c_int32] * 5 + [c_fp], C.c_int),
+    "dpc_spatial_attention": ([c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
+    "dpc_spatial_linear_attention": ([c_fp, c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
+    "dpc_time_embed": ([c_fp] * 8 + [C.c_int32, C.c_int32, c_fp], C.c_int),
+    "dpc_time_proj": ([c_fp] * 4 + [C.c_int32] * 3 + [c_fp], C.c_int),
+    "dpc_ddpm_guided_step": ([c_fp] * 6 + [C.c_int32, C.POINTER(StepCoefs), c_fp, c_fp] + [C.c_int32] * 4 + [c_fp],
+                             C.c_int),
+    "dpc_ddim_guided_step": ([c_fp] * 6 + [C.c_int32, C.POINTER(StepCoefs), c_fp, c_fp] + [C.c_int32] * 4 + [c_fp],
+                             C.c_int),
+    "dpc_predict_x_start": ([c_fp, c_fp, C.c_float, C.c_float, C.c_int32, c_fp, C.c_int64, c_fp], C.c_int),
+}
+
+EXPORTS = tuple(_SIGNATURES)
+
+
+def library_path() -> str:
+    return _SO
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises if the library was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise RuntimeError(
+                f"{_SO} not found: build it with `python -m diffphycon_b200.build` (there is no CPU/PyTorch fallback)")
+        handle = C.CDLL(_SO)
+        for name, (argtypes, restype) in _SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is missing
+            fn.argtypes = argtypes
+            fn.restype = restype
+        if handle.dpc_abi_version() != ABI_VERSION:
+            raise RuntimeError("libdpc_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed: {lib().dpc_last_error().decode()} (rc={rc})")
+
+
+def ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    return t.data_ptr()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class LaunchCounter:
+    """Counts kernel launches issued through this binding (bench.py reports it as gpu_launches)."""
+    count = 0
+
+
+def conv(params: ConvParams, tcgen05: bool = False) -> bool:
+    """Launch a convolution.  With tcgen05=True tries the TMA/tcgen05 kernel first; returns True if it ran.
+    Falls back to the generic tensor-core implicit GEMM only on the documented 'shape not supported' code (-2)."""
+    L = lib()
+    if tcgen05:
+        rc = L.dpc_conv3d_tcgen05(C.byref(params), stream_ptr())
+        if rc == 0:
+            LaunchCounter.count += 1
+            return True
+        if rc != -2:
+            check(rc, "dpc_conv3d_tcgen05")
+    check(L.dpc_conv_igemm(C.byref(params), stream_ptr()), "dpc_conv_igemm")
+    LaunchCounter.count += 1
+    return False
+
+
+def groupnorm_silu(y, stats, gamma, beta, scale_shift, ss_stride, ss_off, residual, out, B, rows_per_sample, Cn, groups,
+                   eps=1e-5):
+    check(lib().dpc_groupnorm_silu(ptr(y), ptr(stats), ptr(gamma), ptr(beta), ptr(scale_shift), ss_stride, ss_off,
+                                   ptr(residual), ptr(out), B, rows_per_sample, Cn, groups, eps, stream_ptr()),
+          "dpc_groupnorm_silu")
+    LaunchCounter.count += 1
+
+
+def layernorm_channels(x, gamma, out, rows, Cn, eps=1e-5):
+    check(lib().dpc_layernorm_channels(ptr(x), ptr(gamma), ptr(out), rows, Cn, eps, stream_ptr()),
+          "dpc_layernorm_channels")
+    LaunchCounter.count += 1
+
+
+def pack_input(x, out, B, F, Ctot, c0, Cin, H, W, Cpad):
+    check(lib().dpc_pack_input(ptr(x), ptr(out), B, F, Ctot, c0, Cin, H, W, Cpad, stream_ptr()), "dpc_pack_input")
+    LaunchCounter.count += 1
+
+
+def temporal_attention(qkv, rope_cos, rope_sin, pos_bias, out, B, F, HW, heads, use_rope=True):
+    check(lib().dpc_temporal_attention(ptr(qkv), ptr(rope_cos), ptr(rope_sin), ptr(pos_bias), ptr(out), B, F, HW, heads,
+                                       1 if use_rope else 0, stream_ptr()), "dpc_temporal_attention")
+    LaunchCounter.count += 1
+
+
+def spatial_attention(qkv, out, BF, HW, heads):
+    check(lib().dpc_spatial_attention(ptr(qkv), ptr(out), BF, HW, heads, stream_ptr()), "dpc_spatial_attention")
+    LaunchCounter.count += 1
+
+
+def spatial_linear_attention(qkv, ctx_ws, out, BF, HW, heads):
+    check(lib().dpc_spatial_linear_attention(ptr(qkv), ptr(ctx_ws), ptr(out), BF, HW, heads, stream_ptr()),
+          "dpc_spatial_linear_attention")
+    LaunchCounter.count += 2
+
+
+def time_embed(t, freqs, w1, b1, w2, b2, hidden_ws, t_emb, B, dim):
+    check(lib().dpc_time_embed(ptr(t), ptr(freqs), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(hidden_ws), ptr(t_emb), B, dim,
+                               stream_ptr()), "dpc_time_embed")
+    LaunchCounter.count += 2
+
+
+def time_proj(t_emb, W, bias, out, B, tdim, total):
+    check(lib().dpc_time_proj(ptr(t_emb), ptr(W), ptr(bias), ptr(out), B, tdim, total, stream_ptr()), "dpc_time_proj")
+    LaunchCounter.count += 1
+
+
+def guided_step(ddim, x, eps_joint, eps_w, noise, init, g, coefs: StepCoefs, x_out, x_start_out, B, F, H, W):
+    fn = lib().dpc_ddim_guided_step if ddim else lib().dpc_ddpm_guided_step
+    check(fn(ptr(x), ptr(eps_joint), ptr(eps_w), ptr(noise), ptr(init), ptr(g), 1 if g is None else 0, C.byref(coefs),
+             ptr(x_out), ptr(x_start_out), B, F, H, W, stream_ptr()), "dpc_guided_step")
+    LaunchCounter.count += 1
+
+
+def predict_x_start(x, eps, sr, srm1, clip, out):
+    check(lib().dpc_predict_x_start(ptr(x), ptr(eps), sr, srm1, 1 if clip else 0, ptr(out), x.numel(), stream_ptr()),
+          "dpc_predict_x_start")
+    LaunchCounter.count += 1

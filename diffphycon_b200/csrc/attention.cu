@@ -1,0 +1,393 @@
+// Attention kernels of Unet3D_with_Conv3D (dim_head = 32, fp32 SIMT arithmetic like the reference's fp32 bmm/einsum):
+//   dpc_temporal_attention        conv3d.py:293-352  (+ RoPE of rotary-embedding-torch 0.8.4, T5 relative bias :74-112)
+//   dpc_spatial_attention         conv3d.py:449-451 + :293-352 (mid block, tokens = pixels of a frame)
+//   dpc_spatial_linear_attention  conv3d.py:243-257
+// qkv rows are channels-last [rows][3*heads*32]: q | k | v thirds, head-major inside a third.
+#include "common.cuh"
+
+namespace dpc {
+
+constexpr int DH = 32;
+constexpr float ATT_SCALE = 0.17677669529663687f;  // 32 ** -0.5 (conv3d.py:286)
+
+// ------------------------------------------------------------------------------------------------------------
+// temporal attention: one warp per (sample, pixel, head); lane i owns query frame(s) i (+32).
+// K and V of all frames live in shared memory (row stride 36 floats: conflict-free float4 stores per quarter-warp,
+// broadcast float4 reads).  Warp shuffles are not needed: every lane runs its own softmax row.
+// ------------------------------------------------------------------------------------------------------------
+template <int R>  // query rows per lane: F <= 32*R
+__global__ void __launch_bounds__(128)
+temporal_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ rope_cos,
+                          const float* __restrict__ rope_sin, const float* __restrict__ pos_bias,
+                          float* __restrict__ out, int64_t total_warps, int F, int HW, int heads, int use_rope) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int LD = DH + 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int FP = 32 * R;
+  float* Ks = sm + (size_t)warp * 2 * FP * LD;
+  float* Vs = Ks + FP * LD;
+  const int C3 = 3 * heads * DH;
+  const int hid = heads * DH;
+
+  for (int64_t wg = (int64_t)blockIdx.x * 4 + warp; wg < total_warps; wg += (int64_t)gridDim.x * 4) {
+    const int head = (int)(wg % heads);
+    const int64_t bp = wg / heads;
+    const int pix = (int)(bp % HW);
+    const int64_t b = bp / HW;
+
+    float q[R][DH];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int f = lane + 32 * r;
+      if (f < F) {
+        const float* row = qkv + (((size_t)b * F + f) * HW + pix) * C3 + head * DH;
+        float kk[DH], vv[DH];
+#pragma unroll
+        for (int c = 0; c < DH; c += 4) {
+          float4 a = __ldcs(reinterpret_cast<const float4*>(row + c));
+          float4 k4 = __ldcs(reinterpret_cast<const float4*>(row + hid + c));
+          float4 v4 = __ldcs(reinterpret_cast<const float4*>(row + 2 * hid + c));
+          q[r][c] = __fmul_rn(a.x, ATT_SCALE); q[r][c + 1] = __fmul_rn(a.y, ATT_SCALE);
+          q[r][c + 2] = __fmul_rn(a.z, ATT_SCALE); q[r][c + 3] = __fmul_rn(a.w, ATT_SCALE);
+          kk[c] = k4.x; kk[c + 1] = k4.y; kk[c + 2] = k4.z; kk[c + 3] = k4.w;
+          vv[c] = v4.x; vv[c + 1] = v4.y; vv[c + 2] = v4.z; vv[c + 3] = v4.w;
+        }
+        if (use_rope) {
+          const float* cs = rope_cos + (size_t)f * DH;
+          const float* sn = rope_sin + (size_t)f * DH;
+#pragma unroll
+          for (int c = 0; c < DH; c += 2) {
+            const float c0 = __ldg(cs + c), s0 = __ldg(sn + c), c1 = __ldg(cs + c + 1), s1 = __ldg(sn + c + 1);
+            // t*cos + rotate_half(t)*sin with rotate_half: (x0, x1) -> (-x1, x0)
+            float q0 = q[r][c], q1 = q[r][c + 1];
+            q[r][c] = __fadd_rn(__fmul_rn(q0, c0), __fmul_rn(-q1, s0));
+            q[r][c + 1] = __fadd_rn(__fmul_rn(q1, c1), __fmul_rn(q0, s1));
+            float k0 = kk[c], k1 = kk[c + 1];
+            kk[c] = __fadd_rn(__fmul_rn(k0, c0), __fmul_rn(-k1, s0));
+            kk[c + 1] = __fadd_rn(__fmul_rn(k1, c1), __fmul_rn(k0, s1));
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < DH; c += 4) {
+          *reinterpret_cast<float4*>(Ks + f * LD + c) = make_float4(kk[c], kk[c + 1], kk[c + 2], kk[c + 3]);
+          *reinterpret_cast<float4*>(Vs + f * LD + c) = make_float4(vv[c], vv[c + 1], vv[c + 2], vv[c + 3]);
+        }
+      }
+    }
+    __syncwarp();
+
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int i = lane + 32 * r;
+      if (i < F) {
+        float s[32 * R];
+        float mx = -INFINITY;
+        const float* brow = pos_bias ? pos_bias + ((size_t)head * F + i) * F : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32 * R; ++j) {
+          if (j < F) {
+            float acc = 0.f;
+#pragma unroll
+            for (int c = 0; c < DH; c += 4) {
+              float4 k4 = *reinterpret_cast<const float4*>(Ks + j * LD + c);
+              acc = fmaf(q[r][c], k4.x, acc);
+              acc = fmaf(q[r][c + 1], k4.y, acc);
+              acc = fmaf(q[r][c + 2], k4.z, acc);
+              acc = fmaf(q[r][c + 3], k4.w, acc);
+            }
+            if (brow) acc += __ldg(brow + j);
+            s[j] = acc;
+            mx = fmaxf(mx, acc);
+          }
+        }
+        float l = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32 * R; ++j) {
+          if (j < F) {
+            s[j] = expf(s[j] - mx);
+            l += s[j];
+          }
+        }
+        const float inv = 1.0f / l;
+        float o[DH];
+#pragma unroll
+        for (int c = 0; c < DH; ++c) o[c] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32 * R; ++j) {
+          if (j < F) {
+            const float pj = s[j] * inv;
+#pragma unroll
+            for (int c = 0; c < DH; c += 4) {
+              float4 v4 = *reinterpret_cast<const float4*>(Vs + j * LD + c);
+              o[c] = fmaf(pj, v4.x, o[c]);
+              o[c + 1] = fmaf(pj, v4.y, o[c + 1]);
+              o[c + 2] = fmaf(pj, v4.z, o[c + 2]);
+              o[c + 3] = fmaf(pj, v4.w, o[c + 3]);
+            }
+          }
+        }
+        float* orow = out + (((size_t)b * F + i) * HW + pix) * hid + head * DH;
+#pragma unroll
+        for (int c = 0; c < DH; c += 4)
+          *reinterpret_cast<float4*>(orow + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// mid-block spatial softmax attention: one thread per query token, K/V streamed through shared memory in tiles of 32
+// tokens with an online softmax.  grid = (ceil(HW/128), heads, B*F).
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+spatial_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int HW, int heads) {
+  __shared__ __align__(16) float Ks[32][DH];
+  __shared__ __align__(16) float Vs[32][DH];
+  const int head = blockIdx.y;
+  const int64_t bf = blockIdx.z;
+  const int tok = blockIdx.x * 128 + threadIdx.x;
+  const int C3 = 3 * heads * DH, hid = heads * DH;
+  const float* base = qkv + (size_t)bf * HW * C3 + head * DH;
+  const bool active = tok < HW;
+  float q[DH], o[DH];
+#pragma unroll
+  for (int c = 0; c < DH; ++c) { q[c] = 0.f; o[c] = 0.f; }
+  if (active) {
+    const float* row = base + (size_t)tok * C3;
+#pragma unroll
+    for (int c = 0; c < DH; c += 4) {
+      float4 a = __ldcs(reinterpret_cast<const float4*>(row + c));
+      q[c] = __fmul_rn(a.x, ATT_SCALE); q[c + 1] = __fmul_rn(a.y, ATT_SCALE);
+      q[c + 2] = __fmul_rn(a.z, ATT_SCALE); q[c + 3] = __fmul_rn(a.w, ATT_SCALE);
+    }
+  }
+  float mx = -INFINITY, l = 0.f;
+  for (int j0 = 0; j0 < HW; j0 += 32) {
+    __syncthreads();
+    // 32 tokens x (32 k + 32 v) floats = 512 float4, 4 per thread
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = threadIdx.x + 128 * i;  // 0..511
+      const int t = idx >> 4, part = idx & 15;     // part 0..7 -> K, 8..15 -> V
+      const int j = j0 + t;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (j < HW) v = __ldg(reinterpret_cast<const float4*>(base + (size_t)j * C3 + (part < 8 ? hid : 2 * hid) + (part & 7) * 4));
+      if (part < 8) *reinterpret_cast<float4*>(&Ks[t][(part & 7) * 4]) = v;
+      else *reinterpret_cast<float4*>(&Vs[t][(part & 7) * 4]) = v;
+    }
+    __syncthreads();
+    if (!active) continue;
+    float s[32];
+    float tmx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < DH; c += 4) {
+        float4 k4 = *reinterpret_cast<const float4*>(&Ks[t][c]);
+        acc = fmaf(q[c], k4.x, acc);
+        acc = fmaf(q[c + 1], k4.y, acc);
+        acc = fmaf(q[c + 2], k4.z, acc);
+        acc = fmaf(q[c + 3], k4.w, acc);
+      }
+      s[t] = (j0 + t < HW) ? acc : -INFINITY;
+      tmx = fmaxf(tmx, s[t]);
+    }
+    const float nmx = fmaxf(mx, tmx);
+    const float corr = expf(mx - nmx);  // first tile: exp(-inf) = 0
+    l *= corr;
+#pragma unroll
+    for (int c = 0; c < DH; ++c) o[c] *= corr;
+#pragma unroll
+    for (int t = 0; t < 32; ++t) {
+      const float pj = expf(s[t] - nmx);  // masked tokens: exp(-inf) = 0
+      l += pj;
+#pragma unroll
+      for (int c = 0; c < DH; c += 4) {
+        float4 v4 = *reinterpret_cast<const float4*>(&Vs[t][c]);
+        o[c] = fmaf(pj, v4.x, o[c]);
+        o[c + 1] = fmaf(pj, v4.y, o[c + 1]);
+        o[c + 2] = fmaf(pj, v4.z, o[c + 2]);
+        o[c + 3] = fmaf(pj, v4.w, o[c + 3]);
+      }
+    }
+    mx = nmx;
+  }
+  if (active) {
+    const float inv = 1.0f / l;
+    float* orow = out + ((size_t)bf * HW + tok) * hid + head * DH;
+#pragma unroll
+    for (int c = 0; c < DH; c += 4)
+      *reinterpret_cast<float4*>(orow + c) = make_float4(o[c] * inv, o[c + 1] * inv, o[c + 2] * inv, o[c + 3] * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// spatial linear attention, pass A: context[d][e] = sum_n softmax_n(k)[d][n] * v[e][n] per (frame, head).
+// One CTA per (frame, head); lane = d, warps stride over pixels; v is read as broadcast float4.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+linattn_context_kernel(const float* __restrict__ qkv, float* __restrict__ ctx, int HW, int heads) {
+  __shared__ float s_red[8][DH];
+  __shared__ float s_max[DH];
+  __shared__ float s_ctx[DH][DH + 1];
+  const int head = blockIdx.x % heads;
+  const int64_t bf = blockIdx.x / heads;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C3 = 3 * heads * DH, hid = heads * DH;
+  const float* kbase = qkv + (size_t)bf * HW * C3 + hid + head * DH;
+  const float* vbase = kbase + hid;
+
+  float mx = -INFINITY;
+  for (int n = warp; n < HW; n += 8) mx = fmaxf(mx, __ldg(kbase + (size_t)n * C3 + lane));
+  s_red[warp][lane] = mx;
+  for (int i = threadIdx.x; i < DH * (DH + 1); i += 256) (&s_ctx[0][0])[i] = 0.f;
+  __syncthreads();
+  if (warp == 0) {
+    float m = s_red[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, s_red[w][lane]);
+    s_max[lane] = m;
+  }
+  __syncthreads();
+  mx = s_max[lane];
+
+  float c[DH];
+#pragma unroll
+  for (int e = 0; e < DH; ++e) c[e] = 0.f;
+  float ksum = 0.f;
+  for (int n = warp; n < HW; n += 8) {
+    const float ek = expf(__ldg(kbase + (size_t)n * C3 + lane) - mx);
+    ksum += ek;
+    const float4* v4p = reinterpret_cast<const float4*>(vbase + (size_t)n * C3);
+#pragma unroll
+    for (int e = 0; e < DH; e += 4) {
+      const float4 v = __ldg(v4p + (e >> 2));
+      c[e] = fmaf(ek, v.x, c[e]);
+      c[e + 1] = fmaf(ek, v.y, c[e + 1]);
+      c[e + 2] = fmaf(ek, v.z, c[e + 2]);
+      c[e + 3] = fmaf(ek, v.w, c[e + 3]);
+    }
+  }
+  __syncthreads();
+  s_red[warp][lane] = ksum;
+  for (int w = 0; w < 8; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int e = 0; e < DH; ++e) s_ctx[lane][e] += c[e];
+    }
+    __syncthreads();
+  }
+  // normalise by sum_n exp(k) and emit
+  float* dst = ctx + (size_t)blockIdx.x * DH * DH;
+  for (int i = threadIdx.x; i < DH * DH; i += 256) {
+    const int d = i >> 5, e = i & 31;
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += s_red[w][d];
+    dst[i] = s_ctx[d][e] / tot;
+  }
+}
+
+// pass B: out[n][e] = sum_d context[d][e] * (softmax_d(q[n])[d] * scale); one thread per (pixel, head).
+__global__ void __launch_bounds__(128)
+linattn_apply_kernel(const float* __restrict__ qkv, const float* __restrict__ ctx, float* __restrict__ out, int HW,
+                     int heads) {
+  __shared__ __align__(16) float s_ctx[DH][DH];
+  const int head = blockIdx.y;
+  const int64_t bf = blockIdx.z;
+  const float* cp = ctx + ((size_t)bf * heads + head) * DH * DH;
+  for (int i = threadIdx.x; i < DH * DH; i += 128) (&s_ctx[0][0])[i] = __ldg(cp + i);
+  __syncthreads();
+  const int tok = blockIdx.x * 128 + threadIdx.x;
+  if (tok >= HW) return;
+  const int C3 = 3 * heads * DH, hid = heads * DH;
+  const float* row = qkv + ((size_t)bf * HW + tok) * C3 + head * DH;
+  float q[DH];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < DH; c += 4) {
+    float4 a = __ldcs(reinterpret_cast<const float4*>(row + c));
+    q[c] = a.x; q[c + 1] = a.y; q[c + 2] = a.z; q[c + 3] = a.w;
+    mx = fmaxf(mx, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
+  }
+  float l = 0.f;
+#pragma unroll
+  for (int c = 0; c < DH; ++c) {
+    q[c] = expf(q[c] - mx);
+    l += q[c];
+  }
+  const float inv = 1.0f / l;
+  float o[DH];
+#pragma unroll
+  for (int e = 0; e < DH; ++e) o[e] = 0.f;
+#pragma unroll
+  for (int d = 0; d < DH; ++d) {
+    const float qs = __fmul_rn(q[d] * inv, ATT_SCALE);
+#pragma unroll
+    for (int e = 0; e < DH; e += 4) {
+      const float4 c4 = *reinterpret_cast<const float4*>(&s_ctx[d][e]);
+      o[e] = fmaf(qs, c4.x, o[e]);
+      o[e + 1] = fmaf(qs, c4.y, o[e + 1]);
+      o[e + 2] = fmaf(qs, c4.z, o[e + 2]);
+      o[e + 3] = fmaf(qs, c4.w, o[e + 3]);
+    }
+  }
+  float* orow = out + ((size_t)bf * HW + tok) * hid + head * DH;
+#pragma unroll
+  for (int e = 0; e < DH; e += 4) *reinterpret_cast<float4*>(orow + e) = make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]);
+}
+
+}  // namespace dpc
+
+extern "C" int dpc_temporal_attention(const float* qkv, const float* rope_cos, const float* rope_sin,
+                                      const float* pos_bias, float* out, int32_t B, int32_t F, int32_t HW,
+                                      int32_t heads, int32_t use_rope, void* stream) {
+  using namespace dpc;
+  DPC_CHECK_ARG(qkv && out && B > 0 && F > 0 && F <= 64 && HW > 0 && heads > 0);
+  DPC_CHECK_ARG(!use_rope || (rope_cos && rope_sin));
+  const int64_t total = (int64_t)B * HW * heads;
+  int64_t blocks = (total + 3) / 4;
+  const int64_t cap = 148LL * 64;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (F <= 32) {
+    const size_t smem = (size_t)4 * 2 * 32 * 36 * sizeof(float);
+    temporal_attention_kernel<1><<<(unsigned)blocks, 128, smem, st>>>(qkv, rope_cos, rope_sin, pos_bias, out, total, F, HW,
+                                                                      heads, use_rope);
+  } else {
+    const size_t smem = (size_t)4 * 2 * 64 * 36 * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+      DPC_CUDA(cudaFuncSetAttribute(temporal_attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    temporal_attention_kernel<2><<<(unsigned)blocks, 128, smem, st>>>(qkv, rope_cos, rope_sin, pos_bias, out, total, F, HW,
+                                                                      heads, use_rope);
+  }
+  DPC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dpc_spatial_attention(const float* qkv, float* out, int32_t BF, int32_t HW, int32_t heads, void* stream) {
+  using namespace dpc;
+  DPC_CHECK_ARG(qkv && out && BF > 0 && BF <= 65535 && HW > 0 && heads > 0);
+  dim3 grid((unsigned)((HW + 127) / 128), (unsigned)heads, (unsigned)BF);
+  spatial_attention_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(qkv, out, HW, heads);
+  DPC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dpc_spatial_linear_attention(const float* qkv, float* ctx_ws, float* out, int32_t BF, int32_t HW,
+                                            int32_t heads, void* stream) {
+  using namespace dpc;
+  DPC_CHECK_ARG(qkv && ctx_ws && out && BF > 0 && BF <= 65535 && HW > 0 && heads > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  linattn_context_kernel<<<(unsigned)((int64_t)BF * heads), 256, 0, st>>>(qkv, ctx_ws, HW, heads);
+  DPC_LAUNCH_CHECK();
+  dim3 grid((unsigned)((HW + 127) / 128), (unsigned)heads, (unsigned)BF);
+  linattn_apply_kernel<<<grid, 128, 0, st>>>(qkv, ctx_ws, out, HW, heads);
+  DPC_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,226 @@
+// HBM-bound elementwise / normalisation kernels of the U-Net (channels-last fp32):
+//   dpc_groupnorm_silu      conv3d.py:197-204, :229-230   (GroupNorm apply + scale/shift + SiLU + residual)
+//   dpc_layernorm_channels  conv3d.py:165-174
+//   dpc_pack_input          conv3d.py:495, smoke.py:612
+// Coalesced 128-bit accesses, grid sized in multiples of the SM count, no shared-memory staging needed (no reuse).
+#include "common.cuh"
+
+namespace dpc {
+
+// One CTA works on a contiguous slab of rows of ONE sample; per-group mean / rstd are derived once per CTA from the
+// double (sum, sumsq) statistics the conv epilogue accumulated.
+template <bool VEC4>
+__global__ void __launch_bounds__(256)
+groupnorm_silu_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, const float* __restrict__ scale_shift, int64_t ss_stride,
+                      int64_t ss_off, const float* __restrict__ residual, float* __restrict__ out,
+                      int64_t rows_per_sample, int C, int groups, float eps, int64_t rows_per_cta) {
+  extern __shared__ __align__(16) float sm[];  // [6][C]: a, o, s1, sh  (per-channel affine after folding mean/rstd)
+  float* s_mul = sm;
+  float* s_sub = sm + C;      // mean per channel
+  float* s_sc = sm + 2 * C;   // scale + 1
+  float* s_sh = sm + 3 * C;   // shift
+  float* s_g = sm + 4 * C;    // gamma
+  float* s_b = sm + 5 * C;    // beta
+  const int b = blockIdx.y;
+  const int cpg = C / groups;
+  const double inv_n = 1.0 / ((double)rows_per_sample * (double)cpg);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpg;
+    const double s = stats[((size_t)b * groups + g) * 2 + 0];
+    const double q = stats[((size_t)b * groups + g) * 2 + 1];
+    const double mean = s * inv_n;
+    double var = q * inv_n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_sub[c] = (float)mean;
+    s_mul[c] = (float)(1.0 / sqrt(var + (double)eps));
+    s_g[c] = gamma[c];
+    s_b[c] = beta[c];
+    if (scale_shift) {
+      s_sc[c] = scale_shift[(size_t)b * ss_stride + ss_off + c] + 1.0f;
+      s_sh[c] = scale_shift[(size_t)b * ss_stride + ss_off + C + c];
+    } else {
+      s_sc[c] = 1.0f;
+      s_sh[c] = 0.0f;
+    }
+  }
+  __syncthreads();
+  const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
+  int64_t r1 = r0 + rows_per_cta;
+  if (r1 > rows_per_sample) r1 = rows_per_sample;
+  const size_t base = ((size_t)b * rows_per_sample + r0) * C;
+  const size_t n = (size_t)(r1 - r0) * C;
+  const bool has_ss = scale_shift != nullptr;
+  if (VEC4) {
+    const float4* y4 = reinterpret_cast<const float4*>(y + base);
+    const float4* r4 = residual ? reinterpret_cast<const float4*>(residual + base) : nullptr;
+    float4* o4 = reinterpret_cast<float4*>(out + base);
+    const size_t n4 = n >> 2;
+    const int c4n = C >> 2;
+    for (size_t i = threadIdx.x; i < n4; i += blockDim.x) {
+      const int c = (int)(i % c4n) * 4;
+      float4 v = __ldcs(y4 + i);
+      float vv[4] = {v.x, v.y, v.z, v.w};
+      const float4 m4 = *reinterpret_cast<const float4*>(s_sub + c);
+      const float4 a4 = *reinterpret_cast<const float4*>(s_mul + c);
+      const float4 g4 = *reinterpret_cast<const float4*>(s_g + c);
+      const float4 b4 = *reinterpret_cast<const float4*>(s_b + c);
+      const float mm[4] = {m4.x, m4.y, m4.z, m4.w}, aa[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float gg[4] = {g4.x, g4.y, g4.z, g4.w}, bb[4] = {b4.x, b4.y, b4.z, b4.w};
+      float sc[4] = {1.f, 1.f, 1.f, 1.f}, sh[4] = {0.f, 0.f, 0.f, 0.f};
+      if (has_ss) {
+        const float4 c4 = *reinterpret_cast<const float4*>(s_sc + c);
+        const float4 h4 = *reinterpret_cast<const float4*>(s_sh + c);
+        sc[0] = c4.x; sc[1] = c4.y; sc[2] = c4.z; sc[3] = c4.w;
+        sh[0] = h4.x; sh[1] = h4.y; sh[2] = h4.z; sh[3] = h4.w;
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float t = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(vv[k], mm[k]), aa[k]), gg[k]), bb[k]);
+        if (has_ss) t = __fadd_rn(__fmul_rn(t, sc[k]), sh[k]);
+        vv[k] = silu_f(t);
+      }
+      if (r4) {
+        float4 r = __ldcs(r4 + i);
+        vv[0] += r.x; vv[1] += r.y; vv[2] += r.z; vv[3] += r.w;
+      }
+      o4[i] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+    }
+  } else {
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const int c = (int)(i % C);
+      float t = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(y[base + i], s_sub[c]), s_mul[c]), s_g[c]), s_b[c]);
+      if (has_ss) t = __fadd_rn(__fmul_rn(t, s_sc[c]), s_sh[c]);
+      t = silu_f(t);
+      if (residual) t += residual[base + i];
+      out[base + i] = t;
+    }
+  }
+}
+
+// one warp per row; two-pass moments in registers (matches torch.var(unbiased=False) / torch.mean)
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+layernorm_channels_kernel(const float* __restrict__ x, const float* __restrict__ gamma, float* __restrict__ out,
+                          int64_t rows, int C, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  float gam[MAXV];
+#pragma unroll
+  for (int j = 0; j < MAXV; ++j) {
+    int c = lane + 32 * j;
+    gam[j] = (c < C) ? gamma[c] : 0.f;
+  }
+  const float invC = 1.0f / (float)C;
+  for (int64_t r = warp_global; r < rows; r += nwarps) {
+    const float* xr = x + (size_t)r * C;
+    float v[MAXV];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      int c = lane + 32 * j;
+      v[j] = (c < C) ? __ldcs(xr + c) : 0.f;
+      s += v[j];
+    }
+    const float mean = warp_sum(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      int c = lane + 32 * j;
+      float d = (c < C) ? (v[j] - mean) : 0.f;
+      q += d * d;
+    }
+    const float var = warp_sum(q) * invC;
+    const float den = sqrtf(var + eps);
+    float* orow = out + (size_t)r * C;
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      int c = lane + 32 * j;
+      if (c < C) orow[c] = __fmul_rn(__fdiv_rn(__fsub_rn(v[j], mean), den), gam[j]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pack_input_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t BF, int Ctot, int c0, int Cin,
+                  int HW, int Cpad) {
+  const int64_t total = BF * HW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t bf = i / HW;
+    const int pix = (int)(i - bf * HW);
+    const float* src = x + ((size_t)bf * Ctot + c0) * HW + pix;
+    float* dst = out + (size_t)i * Cpad;
+    for (int c = 0; c < Cpad; c += 4) {
+      float4 v;
+      v.x = (c + 0 < Cin) ? src[(size_t)(c + 0) * HW] : 0.f;
+      v.y = (c + 1 < Cin) ? src[(size_t)(c + 1) * HW] : 0.f;
+      v.z = (c + 2 < Cin) ? src[(size_t)(c + 2) * HW] : 0.f;
+      v.w = (c + 3 < Cin) ? src[(size_t)(c + 3) * HW] : 0.f;
+      *reinterpret_cast<float4*>(dst + c) = v;
+    }
+  }
+}
+
+}  // namespace dpc
+
+extern "C" int dpc_groupnorm_silu(const float* y, const double* stats, const float* gamma, const float* beta,
+                                  const float* scale_shift, int64_t ss_stride, int64_t ss_off, const float* residual,
+                                  float* out, int32_t B, int64_t rows_per_sample, int32_t C, int32_t groups,
+                                  float eps, void* stream) {
+  using namespace dpc;
+  DPC_CHECK_ARG(y && stats && gamma && beta && out);
+  DPC_CHECK_ARG(B > 0 && rows_per_sample > 0 && C > 0 && groups > 0 && C % groups == 0 && B <= 65535);
+  // enough CTAs for >= 4 waves of 148 SMs x 8 resident CTAs when the tensor is large; at least 2048 rows*C/4 vec per CTA
+  int64_t ctas_per_sample = (148 * 8 * 4 + B - 1) / B;
+  int64_t min_rows = (int64_t)((16384 + C - 1) / C);
+  int64_t rows_per_cta = (rows_per_sample + ctas_per_sample - 1) / ctas_per_sample;
+  if (rows_per_cta < min_rows) rows_per_cta = min_rows;
+  ctas_per_sample = (rows_per_sample + rows_per_cta - 1) / rows_per_cta;
+  dim3 grid((unsigned)ctas_per_sample, (unsigned)B);
+  size_t smem = (size_t)6 * C * sizeof(float);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C % 4 == 0)
+    groupnorm_silu_kernel<true><<<grid, 256, smem, st>>>(y, stats, gamma, beta, scale_shift, ss_stride, ss_off, residual,
+                                                         out, rows_per_sample, C, groups, eps, rows_per_cta);
+  else
+    groupnorm_silu_kernel<false><<<grid, 256, smem, st>>>(y, stats, gamma, beta, scale_shift, ss_stride, ss_off,
+                                                          residual, out, rows_per_sample, C, groups, eps, rows_per_cta);
+  DPC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dpc_layernorm_channels(const float* x, const float* gamma, float* out, int64_t rows, int32_t C,
+                                      float eps, void* stream) {
+  using namespace dpc;
+  DPC_CHECK_ARG(x && gamma && out && rows > 0 && C > 0 && C <= 512);
+  int64_t warps_needed = rows;
+  int64_t blocks = (warps_needed + 7) / 8;
+  const int64_t cap = 148 * 8 * 8;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (C <= 64)
+    layernorm_channels_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, out, rows, C, eps);
+  else if (C <= 128)
+    layernorm_channels_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, out, rows, C, eps);
+  else if (C <= 256)
+    layernorm_channels_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, out, rows, C, eps);
+  else
+    layernorm_channels_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, out, rows, C, eps);
+  DPC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dpc_pack_input(const float* x, float* out, int32_t B, int32_t F, int32_t Ctot, int32_t c0, int32_t Cin,
+                              int32_t H, int32_t W, int32_t Cpad, void* stream) {
+  using namespace dpc;
+  DPC_CHECK_ARG(x && out && B > 0 && F > 0 && H > 0 && W > 0);
+  DPC_CHECK_ARG(Cin > 0 && c0 >= 0 && c0 + Cin <= Ctot && Cpad % 4 == 0 && Cpad >= Cin);
+  const int64_t total = (int64_t)B * F * H * W;
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = 148 * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  pack_input_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, out, (int64_t)B * F, Ctot, c0, Cin, H * W, Cpad);
+  DPC_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,171 @@
+/* dpc_b200.h — C-ABI of the B200-native DiffPhyCon sampling hot path (libdpc_b200.so).
+ *
+ * The reference has no FFI: its boundary for this path is the Python class surface
+ * (SURVEY.md section 8(b)).  This library is what a maintainer would bind from those classes with ctypes
+ * (see INTEGRATION.md).  Every entry point takes plain device pointers + sizes + a CUDA stream handle
+ * (cudaStream_t passed as void*); there are no torch types in any signature.
+ *
+ * Conventions
+ *   - all activation tensors are fp32.  "channels-last" means [B, F, H, W, C] (C contiguous); "reference layout"
+ *     means the reference's [B, F, C, H, W] (diffusion_2d_smoke.py:703, conv3d.py:486).
+ *   - every function returns 0 on success, otherwise a cudaError_t value (or -1 for an argument error);
+ *     dpc_last_error() returns a static string describing the last failure on the calling thread.
+ *   - nothing here synchronises the device; all work is enqueued on `stream`.
+ *
+ * Reference paths are relative to the reference repository root; "conv3d.py" abbreviates
+ * model/video_diffusion_pytorch/video_diffusion_pytorch_conv3d.py and "smoke.py" diffusion/diffusion_2d_smoke.py.
+ */
+#ifndef DPC_B200_H
+#define DPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DPC_ABI_VERSION 1
+
+int dpc_abi_version(void);
+const char* dpc_last_error(void);
+/* 1 if the current device is sm_100 (B200), else 0; negative on CUDA error. */
+int dpc_device_is_sm100(void);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Implicit-GEMM convolution / linear layer on tensor cores (TF32 inputs, fp32 accumulate).
+ * Replaces nn.Conv3d / nn.ConvTranspose3d / nn.Linear / 1x1 nn.Conv2d forward calls of
+ * conv3d.py:159-163 (Up/Downsample), :189-204 (Block.proj), :214 (res_conv), :240-241, :288-289 (to_qkv/to_out),
+ * :403 (init_conv), :471 (final 1x1x1).
+ *
+ * Input  : x1 [B,Fi,Hi,Wi,C1] channels-last, optionally concatenated along C with x2 [B,Fi,Hi,Wi,C2]
+ *          (replaces torch.cat at conv3d.py:538, :545).
+ * Weights: packed K-major [Npad][Kpad], k = tap*(C1+C2) + ci, tap = (dt*kh + dh)*kw + dw, zero padded
+ *          (packing is done by the host mirror, diffphycon_b200/packing.py).
+ * taps   : device int32 [ntaps][4] = (dt, dh, dw, (dt*Hi + dh)*Wi + dw).
+ * Output : row m = ((b*Fo + fo)*Ho + ho)*Wo + wo is written to
+ *          channels-last row ((b*Fo + fo)*Hfull + ho*oh_mul + oh_off)*Wfull + wo*ow_mul + ow_off   (out_layout 0)
+ *          or to reference layout [B,Fo,Cout,Hfull,Wfull]                                            (out_layout 1).
+ *          oh_mul/ow_mul = 2 express one parity class of ConvTranspose3d(1,4,4; stride (1,2,2); pad (0,1,1)).
+ * Epilogue: + bias[Cout], + residual (same indexing as the output, channels-last only),
+ *          GroupNorm partial statistics: gn_stats[b][g][0..1] += (sum, sum of squares) over the written values,
+ *          g = n / (Cout / gn_groups)   (feeds dpc_groupnorm_silu; replaces the statistics pass of nn.GroupNorm).
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct dpc_conv_params {
+  const float* x1; const float* x2;
+  const float* w; const float* bias; const float* residual;
+  const int32_t* taps;
+  float* y;
+  double* gn_stats;
+  int32_t C1, C2;
+  int32_t B, Fi, Hi, Wi;
+  int32_t Fo, Ho, Wo;
+  int32_t ntaps;
+  int32_t st, sh, sw;
+  int32_t pt, ph, pw;
+  int32_t Cout, Npad, Kpad;
+  int32_t Hfull, Wfull, oh_mul, oh_off, ow_mul, ow_off;
+  int32_t out_layout;
+  int32_t gn_groups;
+  int32_t precise;   /* 1 = 3xTF32 error-compensated product (near-fp32), 0 = plain TF32 */
+} dpc_conv_params;
+
+int dpc_conv_igemm(const dpc_conv_params* p, void* stream);
+
+/* 3x3x3 / pad 1 Conv3d on the 5th-generation tensor cores: TMA-tiled operand staging, tcgen05.mma (kind::tf32)
+ * with the accumulator in TMEM.  Same arguments and epilogue as dpc_conv_igemm; requires ntaps == 27, unit stride,
+ * C1 % 32 == 0, C2 % 32 == 0, Cout % 16 == 0, Cout <= 256, (Ho*Wo) % 128 == 0 or 128 % Wo == 0.
+ * `w` must be packed [27][Cout][Cin] (tap-major, K contiguous).  Returns -2 if the shape is not supported so the
+ * host mirror can fall back to dpc_conv_igemm (same numerics class). */
+int dpc_conv3d_tcgen05(const dpc_conv_params* p, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * GroupNorm-apply + (scale+1, shift) + SiLU (+ residual) — conv3d.py:197-204 (Block.forward after proj),
+ * :229-230 (ResnetBlock residual add).  y is the raw conv output [B, rows_per_sample, C] channels-last,
+ * stats is the [B,G,2] double buffer filled by the conv epilogue.  scale_shift (nullable) is [B, ss_stride]
+ * with scale at [ss_off .. ss_off+C) and shift at [ss_off+C .. ss_off+2C)   (conv3d.py:222-225).
+ * out = silu(((y-mean)*rstd*gamma + beta) * (scale+1) + shift) + residual
+ * ------------------------------------------------------------------------------------------------------- */
+int dpc_groupnorm_silu(const float* y, const double* stats, const float* gamma, const float* beta,
+                       const float* scale_shift, int64_t ss_stride, int64_t ss_off,
+                       const float* residual, float* out,
+                       int32_t B, int64_t rows_per_sample, int32_t C, int32_t groups, float eps, void* stream);
+
+/* Channel LayerNorm, gain only: (x-mean)/sqrt(var+eps)*gamma over C for every row — conv3d.py:165-174. */
+int dpc_layernorm_channels(const float* x, const float* gamma, float* out, int64_t rows, int32_t C, float eps,
+                           void* stream);
+
+/* Reference layout [B,F,Ctot,H,W], channels [c0, c0+Cin) -> channels-last [B,F,H,W,Cpad] zero padded
+ * (replaces the permute at conv3d.py:495 and the slice x[:, :, 3:5] at smoke.py:612). */
+int dpc_pack_input(const float* x, float* out, int32_t B, int32_t F, int32_t Ctot, int32_t c0, int32_t Cin,
+                   int32_t H, int32_t W, int32_t Cpad, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Attention blocks.  qkv is [rows, 3*heads*32] channels-last with q | k | v thirds, head-major inside each third
+ * (conv3d.py:246, :311); out is [rows, heads*32].  dim_head is fixed at 32 (conv3d.py:362).
+ * ------------------------------------------------------------------------------------------------------- */
+/* Temporal softmax attention over frames per pixel with RoPE on q,k and T5 relative bias — conv3d.py:293-352,
+ * rotary-embedding-torch 0.8.4 rotate_queries_or_keys.  rope_cos/rope_sin: [F][32] (angle table, interleaved pairs);
+ * pos_bias: [heads][F][F] or NULL; use_rope 0 skips the rotation. F <= 64. */
+int dpc_temporal_attention(const float* qkv, const float* rope_cos, const float* rope_sin, const float* pos_bias,
+                           float* out, int32_t B, int32_t F, int32_t HW, int32_t heads, int32_t use_rope,
+                           void* stream);
+/* Softmax attention over the HW tokens of every frame (mid block) — conv3d.py:449-451 with Attention(:293-352),
+ * no RoPE, no bias. */
+int dpc_spatial_attention(const float* qkv, float* out, int32_t BF, int32_t HW, int32_t heads, void* stream);
+/* Spatial linear attention — conv3d.py:243-257: q softmax over d, k softmax over pixels, v NOT divided by HW.
+ * ctx_ws: workspace of BF*heads*32*32 floats. */
+int dpc_spatial_linear_attention(const float* qkv, float* ctx_ws, float* out, int32_t BF, int32_t HW, int32_t heads,
+                                 void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Time embedding — conv3d.py:139-151 (SinusoidalPosEmb), :404-409 (time_mlp), :211-214, :222-224 (ResnetBlock.mlp).
+ * freqs: [dim/2] table exp(-i*log(10000)/(dim/2-1)).  t_emb out: [B, 4*dim].
+ * dpc_time_proj: out[b, j] = bias[j] + sum_k W[j,k] * silu(t_emb[b,k]) for the row-concatenated mlp weights of all
+ * ResnetBlocks (W: [total, tdim]).
+ * ------------------------------------------------------------------------------------------------------- */
+int dpc_time_embed(const int64_t* t, const float* freqs, const float* w1, const float* b1, const float* w2,
+                   const float* b2, float* hidden_ws, float* t_emb, int32_t B, int32_t dim, void* stream);
+int dpc_time_proj(const float* t_emb, const float* W, const float* bias, float* out, int32_t B, int32_t tdim,
+                  int32_t total, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * Fused guidance + posterior update of one denoising step, reference layout [B,F,6,H,W].
+ * smoke.py:610-656 (model_predictions), :659-666 (p_mean_variance), :671-699 (p_sample), :720 (re-impose init),
+ * with the stock guidance of inference/inference_2d_smoke.py:30-44 in closed form.
+ * ------------------------------------------------------------------------------------------------------- */
+typedef struct dpc_step_coefs {
+  float sqrt_recip_alphas_cumprod;    /* extract(sqrt_recip_alphas_cumprod, t) */
+  float sqrt_recipm1_alphas_cumprod;
+  float guidance_coef;                /* standard_fixed_ratio, or coeff_ratio*flip(betas)[t] ("standard-alpha") */
+  float prior_coef;                   /* w_prob_exp - 1 */
+  float w_energy;                     /* stock guidance_fn argument */
+  float rescaler[6];                  /* dataset/data_2d.py:167 */
+  /* DDPM posterior (used by dpc_ddpm_guided_step) */
+  float posterior_mean_coef1, posterior_mean_coef2, sigma;   /* sigma = exp(0.5*posterior_log_variance_clipped) */
+  int32_t add_noise;                  /* t > 0 */
+  /* DDIM (used by dpc_ddim_guided_step) */
+  float sqrt_alpha_next, c, ddim_sigma;
+  int32_t last;                       /* time_next < 0: return x_start */
+} dpc_step_coefs;
+
+/* eps_joint [B,F,6,H,W]; eps_w [B,F,2,H,W] (scattered into channels 3:5); noise like x (may be NULL when
+ * add_noise == 0); init [B,H,W] or NULL (NULL: do not re-impose x[:,0,0]); x_out like x (may alias x);
+ * x_start_out nullable.
+ * use_stock_guidance 0: `g` [B,F,6,H,W] is a user-supplied design_fn gradient evaluated on x_start (see
+ * dpc_predict_x_start). */
+int dpc_ddpm_guided_step(const float* x, const float* eps_joint, const float* eps_w, const float* noise,
+                         const float* init, const float* g, int32_t use_stock_guidance,
+                         const dpc_step_coefs* coefs, float* x_out, float* x_start_out,
+                         int32_t B, int32_t F, int32_t H, int32_t W, void* stream);
+int dpc_ddim_guided_step(const float* x, const float* eps_joint, const float* eps_w, const float* noise,
+                         const float* init, const float* g, int32_t use_stock_guidance,
+                         const dpc_step_coefs* coefs, float* x_out, float* x_start_out,
+                         int32_t B, int32_t F, int32_t H, int32_t W, void* stream);
+/* x_start = maybe_clip(sqrt_recip*x - sqrt_recipm1*eps) — smoke.py:576-580, :620-621; for user design_fn callables. */
+int dpc_predict_x_start(const float* x, const float* eps, float sqrt_recip, float sqrt_recipm1, int32_t clip,
+                        float* x_start, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPC_B200_H */

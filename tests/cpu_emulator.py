@@ -1,0 +1,216 @@
+"""TEST INFRASTRUCTURE: a CPU emulation of the C-ABI entry points of libdpc_b200.so, written with torch ops.
+
+It lets the CPU test suite run the HOST logic of diffphycon_b200 (weight packing, tap tables, transposed-conv parity
+classes, buffer orchestration, scale/shift offsets, sampler coefficients) against the golden vectors without a GPU.
+It is installed by monkeypatching `diffphycon_b200._lib` inside tests only; the product never imports this file and
+has no CPU path.  Each emulator follows the contract documented in include/dpc_b200.h.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from oracle import unet3d_oracle as uo
+
+HEADS_DIM = 32
+
+
+def _view(ptr, numel, dtype=np.float32):
+    if not ptr:
+        return None
+    ctype = {np.float32: ctypes.c_float, np.float64: ctypes.c_double, np.int32: ctypes.c_int32}[dtype]
+    arr = np.ctypeslib.as_array((ctype * numel).from_address(ptr))
+    return torch.from_numpy(arr)
+
+
+def conv(p, tcgen05=False):
+    B, Fi, Hi, Wi, C1, C2 = p.B, p.Fi, p.Hi, p.Wi, p.C1, p.C2
+    Fo, Ho, Wo = p.Fo, p.Ho, p.Wo
+    cin = C1 + C2
+    x = _view(p.x1, B * Fi * Hi * Wi * C1).reshape(B, Fi, Hi, Wi, C1)
+    if C2:
+        x2 = _view(p.x2, B * Fi * Hi * Wi * C2).reshape(B, Fi, Hi, Wi, C2)
+        x = torch.cat([x, x2], dim=-1)
+    w = _view(p.w, p.Npad * p.Kpad).reshape(p.Npad, p.Kpad)
+    taps = _view(p.taps, p.ntaps * 4, np.int32).reshape(p.ntaps, 4)
+    acc = torch.zeros(B, Fo, Ho, Wo, p.Cout, dtype=torch.float64)
+    fo = torch.arange(Fo)
+    ho = torch.arange(Ho)
+    wo = torch.arange(Wo)
+    for t in range(p.ntaps):
+        dt, dh, dw, delta = [int(v) for v in taps[t]]
+        assert delta == (dt * Hi + dh) * Wi + dw
+        fi = fo * p.st + dt - p.pt
+        hi = ho * p.sh + dh - p.ph
+        wi = wo * p.sw + dw - p.pw
+        vf, vh, vw = (fi >= 0) & (fi < Fi), (hi >= 0) & (hi < Hi), (wi >= 0) & (wi < Wi)
+        g = x[:, fi.clamp(0, Fi - 1)][:, :, hi.clamp(0, Hi - 1)][:, :, :, wi.clamp(0, Wi - 1)]
+        mask = (vf[:, None, None] & vh[None, :, None] & vw[None, None, :]).to(g.dtype)
+        g = g * mask[None, :, :, :, None]
+        wt = w[: p.Cout, t * cin:(t + 1) * cin].double()
+        acc += g.double() @ wt.t()
+    if p.bias:
+        acc += _view(p.bias, p.Cout).double()
+    Hf, Wf = p.Hfull, p.Wfull
+    hs = slice(p.oh_off, Hf, p.oh_mul)
+    ws = slice(p.ow_off, Wf, p.ow_mul)
+    if p.out_layout == 0:
+        y = _view(p.y, B * Fo * Hf * Wf * p.Cout).reshape(B, Fo, Hf, Wf, p.Cout)
+        if p.residual:
+            r = _view(p.residual, B * Fo * Hf * Wf * p.Cout).reshape(B, Fo, Hf, Wf, p.Cout)
+            acc += r[:, :, hs, ws].double()
+        y[:, :, hs, ws] = acc.float()
+    else:
+        y = _view(p.y, B * Fo * Hf * Wf * p.Cout).reshape(B, Fo, p.Cout, Hf, Wf)
+        y[:, :, :, hs, ws] = acc.float().permute(0, 1, 4, 2, 3)
+    if p.gn_stats:
+        G = p.gn_groups
+        st = _view(p.gn_stats, B * G * 2, np.float64).reshape(B, G, 2)
+        v = acc.float().double().reshape(B, -1, G, p.Cout // G)
+        st[:, :, 0] += v.sum(dim=(1, 3))
+        st[:, :, 1] += (v * v).sum(dim=(1, 3))
+    return False
+
+
+def groupnorm_silu(y, stats, gamma, beta, scale_shift, ss_stride, ss_off, residual, out, B, rps, Cn, groups, eps=1e-5):
+    v = y[: B * rps * Cn].reshape(B, rps, groups, Cn // groups)
+    st = stats[: B * groups * 2].reshape(B, groups, 2)
+    n = rps * (Cn // groups)
+    mean = st[:, :, 0] / n
+    var = (st[:, :, 1] / n - mean * mean).clamp(min=0)
+    rstd = (1.0 / torch.sqrt(var + eps)).float()
+    t = (v - mean.float()[:, None, :, None]) * rstd[:, None, :, None]
+    t = t.reshape(B, rps, Cn) * gamma + beta
+    if scale_shift is not None:
+        ss = scale_shift[: B * ss_stride].reshape(B, ss_stride)
+        t = t * (ss[:, None, ss_off:ss_off + Cn] + 1) + ss[:, None, ss_off + Cn:ss_off + 2 * Cn]
+    t = torch.nn.functional.silu(t)
+    if residual is not None:
+        t = t + residual[: B * rps * Cn].reshape(B, rps, Cn)
+    out[: B * rps * Cn] = t.reshape(-1)
+
+
+def layernorm_channels(x, gamma, out, rows, Cn, eps=1e-5):
+    v = x[: rows * Cn].reshape(rows, Cn)
+    mean = v.mean(dim=1, keepdim=True)
+    var = v.var(dim=1, unbiased=False, keepdim=True)
+    out[: rows * Cn] = ((v - mean) / (var + eps).sqrt() * gamma).reshape(-1)
+
+
+def pack_input(x, out, B, F, Ctot, c0, Cin, H, W, Cpad):
+    v = x.reshape(B, F, Ctot, H, W)[:, :, c0:c0 + Cin].permute(0, 1, 3, 4, 2)
+    o = torch.zeros(B, F, H, W, Cpad)
+    o[..., :Cin] = v
+    out[: o.numel()] = o.reshape(-1)
+
+
+def _split_heads(qkv, heads):
+    hid = heads * HEADS_DIM
+    q, k, v = qkv[..., :hid], qkv[..., hid:2 * hid], qkv[..., 2 * hid:]
+    f = lambda t: t.reshape(*t.shape[:-1], heads, HEADS_DIM).transpose(-2, -3)  # ... h n d
+    return f(q), f(k), f(v)
+
+
+def temporal_attention(qkv, rope_cos, rope_sin, pos_bias, out, B, F, HW, heads, use_rope=True):
+    hid = heads * HEADS_DIM
+    t = qkv[: B * F * HW * 3 * hid].reshape(B, F, HW, 3 * hid).permute(0, 2, 1, 3)  # b hw f c
+    q, k, v = _split_heads(t, heads)
+    q = q * (HEADS_DIM ** -0.5)
+    if use_rope:
+        def rot(u):
+            x = u.reshape(*u.shape[:-1], HEADS_DIM // 2, 2)
+            x1, x2 = x.unbind(-1)
+            r = torch.stack((-x2, x1), dim=-1).reshape(u.shape)
+            return u * rope_cos + r * rope_sin
+        q, k = rot(q), rot(k)
+    sim = torch.einsum("...hid,...hjd->...hij", q, k)
+    if pos_bias is not None:
+        sim = sim + pos_bias
+    o = torch.einsum("...hij,...hjd->...hid", sim.softmax(-1), v)
+    o = o.transpose(-2, -3).reshape(B, HW, F, hid).permute(0, 2, 1, 3)
+    out[: o.numel()] = o.reshape(-1)
+
+
+def spatial_attention(qkv, out, BF, HW, heads):
+    hid = heads * HEADS_DIM
+    t = qkv[: BF * HW * 3 * hid].reshape(BF, HW, 3 * hid)
+    q, k, v = _split_heads(t, heads)
+    sim = torch.einsum("bhid,bhjd->bhij", q * (HEADS_DIM ** -0.5), k)
+    o = torch.einsum("bhij,bhjd->bhid", sim.softmax(-1), v).transpose(1, 2).reshape(BF, HW, hid)
+    out[: o.numel()] = o.reshape(-1)
+
+
+def spatial_linear_attention(qkv, ctx_ws, out, BF, HW, heads):
+    hid = heads * HEADS_DIM
+    t = qkv[: BF * HW * 3 * hid].reshape(BF, HW, 3 * hid)
+    q, k, v = _split_heads(t, heads)  # b h n d
+    q = q.softmax(dim=-1) * (HEADS_DIM ** -0.5)
+    k = k.softmax(dim=-2)
+    ctx = torch.einsum("bhnd,bhne->bhde", k, v)
+    o = torch.einsum("bhde,bhnd->bhne", ctx, q).transpose(1, 2).reshape(BF, HW, hid)
+    out[: o.numel()] = o.reshape(-1)
+
+
+def time_embed(t, freqs, w1, b1, w2, b2, hidden_ws, t_emb, B, dim):
+    arg = t.float()[:, None] * freqs[None, :]
+    emb = torch.cat((arg.sin(), arg.cos()), dim=-1)
+    h = torch.nn.functional.gelu(emb @ w1.t() + b1)
+    t_emb[: B * dim * 4] = (h @ w2.t() + b2).reshape(-1)
+
+
+def time_proj(t_emb, W, bias, out, B, tdim, total):
+    e = torch.nn.functional.silu(t_emb[: B * tdim].reshape(B, tdim))
+    out[: B * total] = (e @ W.t() + bias).reshape(-1)
+
+
+def predict_x_start(x, eps, sr, srm1, clip, out):
+    v = np.float32(sr) * x - np.float32(srm1) * eps
+    out.copy_(v.clamp(-1, 1) if clip else v)
+
+
+def guided_step(ddim, x, eps_joint, eps_w, noise, init, g, c, x_out, x_start_out, B, F, H, W):
+    f32 = lambda v: torch.tensor(v, dtype=torch.float32)
+    sr, srm1 = f32(c.sqrt_recip_alphas_cumprod), f32(c.sqrt_recipm1_alphas_cumprod)
+    clip = (lambda v: v.clamp(-1, 1)) if ddim else (lambda v: v)
+    ew = torch.zeros_like(eps_joint)
+    ew[:, :, 3:5] = eps_w
+    xs0 = clip(sr * x - srm1 * eps_joint)
+    if g is None:
+        R = torch.tensor(list(c.rescaler), dtype=torch.float32).reshape(1, 1, 6, 1, 1)
+        g = torch.zeros_like(x)
+        g[:, -1, 5] = -(1.0 / (H * W))
+        g[:, :, 3:5] = (f32(c.w_energy) / f32(float(F * 2 * H * W))) * (2.0 * (xs0 * R)[:, :, 3:5])
+    pn = eps_joint + (f32(c.guidance_coef) * g + f32(c.prior_coef) * ew)
+    xs = clip(sr * x - srm1 * pn)
+    if ddim:
+        pn = (sr * x - xs) / srm1
+        if c.last:
+            o = xs
+        else:
+            o = xs * f32(c.sqrt_alpha_next) + f32(c.c) * pn + f32(c.ddim_sigma) * noise
+    else:
+        xs = xs.clamp(-1, 1)
+        o = f32(c.posterior_mean_coef1) * xs + f32(c.posterior_mean_coef2) * x
+        if c.add_noise:
+            o = o + f32(c.sigma) * noise
+    if init is not None and not (ddim and c.last):
+        o = o.clone()
+        o[:, 0, 0] = init
+    x_out.copy_(o)
+    if x_start_out is not None:
+        x_start_out.copy_(xs)
+
+
+def install(monkeypatch):
+    """Route diffphycon_b200._lib's launch wrappers to the emulators above (tests only)."""
+    from diffphycon_b200 import _lib
+    for name in ("conv", "groupnorm_silu", "layernorm_channels", "pack_input", "temporal_attention",
+                 "spatial_attention", "spatial_linear_attention", "time_embed", "time_proj", "predict_x_start",
+                 "guided_step"):
+        monkeypatch.setattr(_lib, name, globals()[name])
+    monkeypatch.setattr(_lib, "stream_ptr", lambda: None)
+
+
+_ = uo  # the oracle is imported so that a missing oracle fails loudly at collection time
