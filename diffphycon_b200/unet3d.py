@@ -236,7 +236,6 @@ class Unet3D_with_Conv3D(nn.Module):
         self.micro_batch: Optional[int] = None  # samples per pass through the network (None = whole batch)
         self._packed = None
         self._packed_key = None
-        self._pools: Dict[torch.device, _Pool] = {}
         self._geo_cache: Dict[tuple, dict] = {}
         self.taps: Optional[dict] = None  # set to {} to capture named intermediates (NCDHW copies) for parity tests
 
@@ -413,10 +412,12 @@ class Unet3D_with_Conv3D(nn.Module):
             self._forward_chunk(x_full[b0:b1], time[b0:b1], out[b0:b1], c0, x_full.shape[2])
         return out
 
+    _pools: Dict[torch.device, _Pool] = {}   # one buffer pool per device, shared by every network instance
+
     def _pool(self, device) -> _Pool:
-        p = self._pools.get(device)
+        p = Unet3D_with_Conv3D._pools.get(device)
         if p is None:
-            p = self._pools[device] = _Pool(device)
+            p = Unet3D_with_Conv3D._pools[device] = _Pool(device)
         return p
 
     def _forward_chunk(self, x, time, out, c0, ctot):

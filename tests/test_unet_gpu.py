@@ -1,0 +1,111 @@
+"""GPU parity of the whole U-Net forward (through the C-ABI kernels) against the golden vectors produced by the
+unmodified reference, in both numerics modes, plus size-independent properties at the metric configuration's shape.
+  tf32   : contraction-class tolerance 1e-2 of the output scale (54 chained TF32 convs, 10-bit mantissa operands)
+  3xtf32 : fp32-class tolerance 2e-4"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import diffphycon_b200 as dpc
+from oracle import unet3d_oracle as uo
+
+pytestmark = pytest.mark.gpu
+
+CASES = {
+    "unet_small_c6": dict(dim=32, dim_mults=(1, 2), channels=6),
+    "unet_small_c2": dict(dim=32, dim_mults=(1, 2), channels=2),
+    "unet_smoke_arch": dict(dim=64, dim_mults=(1, 2, 4), channels=6),
+    "unet_jelly_arch": dict(dim=32, dim_mults=(1, 2), channels=7, out_dim=4),
+}
+TOL = {"tf32": 1e-2, "3xtf32": 2e-4}
+
+
+def build(name, seed, precision, tcgen05=True):
+    cfg = uo.UnetCfg(**CASES[name])
+    net = dpc.Unet3D_with_Conv3D(**CASES[name])
+    net.load_state_dict(uo.make_params(cfg, seed), strict=True)
+    net.precision = precision
+    net.use_tcgen05 = tcgen05
+    return net.cuda()
+
+
+@pytest.mark.parametrize("precision", ["3xtf32", "tf32"])
+@pytest.mark.parametrize("name", list(CASES))
+def test_unet_forward_matches_reference_golden(name, precision, golden_dir):
+    z = np.load(os.path.join(golden_dir, name + ".npz"))
+    net = build(name, int(z["seed"]), precision)
+    net.taps = {}
+    y = net(torch.from_numpy(z["x"]).cuda(), torch.from_numpy(z["t"]).cuda()).cpu()
+    ref = torch.from_numpy(z["y"])
+    assert y.shape == ref.shape
+    for k in z.files:
+        if k.startswith("act/"):
+            a = torch.from_numpy(z[k])
+            err = (net.taps[k[4:]].cpu() - a).abs().max().item() / max(1.0, a.abs().max().item())
+            assert err <= TOL[precision], (k, err)
+    err = (y - ref).abs().max().item() / max(1.0, ref.abs().max().item())
+    assert err <= TOL[precision], err
+
+
+def test_unet_forward_vs_oracle_smoke_arch_32px():
+    """Larger-than-golden case checked against the CPU oracle run here: smoke architecture, 8 frames, 32x32."""
+    cfg = uo.UnetCfg(dim=64, dim_mults=(1, 2, 4), channels=6)
+    params = uo.make_params(cfg, 21)
+    g = torch.Generator().manual_seed(22)
+    x = torch.randn(2, 8, 6, 32, 32, generator=g)
+    t = torch.tensor([17, 940])
+    ref = uo.forward(params, cfg, x, t)
+    for precision in ("3xtf32", "tf32"):
+        net = dpc.Unet3D_with_Conv3D(dim=64, dim_mults=(1, 2, 4), channels=6)
+        net.load_state_dict(params)
+        net.precision = precision
+        y = net.cuda()(x.cuda(), t.cuda()).cpu()
+        err = (y - ref).abs().max().item() / max(1.0, ref.abs().max().item())
+        assert err <= TOL[precision], (precision, err)
+
+
+def test_micro_batch_and_batch_independence():
+    net = build("unet_small_c6", 5, "tf32")
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(3, 4, 6, 16, 16, generator=g).cuda()
+    t = torch.tensor([3, 500, 999]).cuda()
+    y = net(x, t)
+    net.micro_batch = 1
+    y1 = net(x, t)
+    # trajectories never interact: per-sample results do not depend on batch composition
+    assert torch.allclose(y, y1, atol=1e-6, rtol=0)
+    y2 = net(x[1:2], t[1:2])
+    assert torch.allclose(y[1:2], y2, atol=1e-6, rtol=0)
+
+
+def test_forward_slice_equals_forward_on_slice():
+    net = build("unet_small_c2", 7, "tf32")
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 4, 6, 16, 16, generator=g).cuda()
+    t = torch.tensor([10, 700]).cuda()
+    a = net(x[:, :, 3:5].contiguous(), t)
+    b = torch.empty_like(a)
+    net.forward_slice(x, 3, t, b)
+    assert torch.equal(a, b)
+
+
+def test_metric_shape_forward_properties():
+    """One sample at the metric configuration's shape (32 frames, 64x64, smoke architecture): finite output, correct
+    shape, deterministic, and equal in tcgen05 and generic tensor-core paths within TF32 accumulation-order noise."""
+    cfg = uo.UnetCfg(dim=64, dim_mults=(1, 2, 4), channels=6)
+    params = uo.make_params(cfg, 31)
+    net = dpc.Unet3D_with_Conv3D(dim=64, dim_mults=(1, 2, 4), channels=6)
+    net.load_state_dict(params)
+    net = net.cuda()
+    g = torch.Generator().manual_seed(32)
+    x = torch.randn(1, 32, 6, 64, 64, generator=g).cuda()
+    t = torch.tensor([321]).cuda()
+    y = net(x, t)
+    assert y.shape == (1, 32, 6, 64, 64) and torch.isfinite(y).all()
+    assert torch.equal(y, net(x, t))
+    net.use_tcgen05 = False
+    y_generic = net(x, t)
+    scale = y_generic.abs().max().item()
+    assert (y - y_generic).abs().max().item() <= 2e-3 * max(1.0, scale)
