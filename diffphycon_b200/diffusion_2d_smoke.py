@@ -252,32 +252,42 @@ class GaussianDiffusion(nn.Module):
         img = torch.randn(shape, device=device)
         init = init.to(device).float().contiguous()
         img[:, 0, 0] = init
-        s = self._sched()
-        b, f, ch, h, w = shape
         it = time_pairs
         if self.progress:
             from tqdm.auto import tqdm
             it = tqdm(time_pairs, desc='sampling loop time step')
         for time, time_next in it:
-            c = self._coefs(time, design_fn, design_guidance)
-            eps_j, eps_w = self._eps(img, time)
-            g = None
-            if not isinstance(design_fn, StockSmokeGuidance):
-                g = self._user_gradient(img, eps_j, c, True, design_fn, low, init, init_u)
-            noise = None
-            if time_next < 0:
-                c.last = 1
-            else:
-                alpha = s['alphas_cumprod'][time]
-                alpha_next = s['alphas_cumprod'][time_next]
-                sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
-                cc = (1 - alpha_next - sigma ** 2).sqrt()
-                c.sqrt_alpha_next, c.c, c.ddim_sigma, c.last = float(alpha_next.sqrt()), float(cc), float(sigma), 0
-                noise = torch.randn_like(img)
-            out = torch.empty_like(img)
-            _lib.guided_step(True, img, eps_j, eps_w, noise, init, g, c, out, None, b, f, h, w)
-            img = out
+            img = self.ddim_step(img, time, time_next, design_fn=design_fn, design_guidance=design_guidance, init=init,
+                                 init_u=init_u, low=low)
         return img
+
+    @torch.no_grad()
+    def ddim_step(self, img, time: int, time_next: int, design_fn=None, design_guidance="standard", init=None,
+                  init_u=None, low=None, noise=None):
+        """One iteration of the DDIM loop, smoke.py:739-775 (model_predictions with clip_x_start=True,
+        rederive_pred_noise=True).  `noise` defaults to torch.randn_like(img) drawn where the reference draws it."""
+        b, f, ch, h, w = img.shape
+        s = self._sched()
+        eta = self.ddim_sampling_eta
+        c = self._coefs(time, design_fn, design_guidance)
+        eps_j, eps_w = self._eps(img, time)
+        g = None
+        if not isinstance(design_fn, StockSmokeGuidance):
+            g = self._user_gradient(img, eps_j, c, True, design_fn, low, init, init_u)
+        if time_next < 0:
+            c.last = 1
+            noise = None
+        else:
+            alpha = s['alphas_cumprod'][time]
+            alpha_next = s['alphas_cumprod'][time_next]
+            sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+            cc = (1 - alpha_next - sigma ** 2).sqrt()
+            c.sqrt_alpha_next, c.c, c.ddim_sigma, c.last = float(alpha_next.sqrt()), float(cc), float(sigma), 0
+            if noise is None:
+                noise = torch.randn_like(img)
+        out = torch.empty_like(img)
+        _lib.guided_step(True, img.contiguous(), eps_j, eps_w, noise, init, g, c, out, None, b, f, h, w)
+        return out
 
     @torch.no_grad()
     def sample(self, batch_size=16, design_fn=None, design_guidance="standard", init=None, init_u=None, control=None,

@@ -156,9 +156,26 @@ def gen_sampler():
     diff = d.GaussianDiffusion([mj, mw], image_size=S, frames=Fr, timesteps=1000, sampling_timesteps=3,
                                ddim_sampling_eta=1.0, standard_fixed_ratio=1e5, coeff_ratio=0.0, eval_2ddpm=True,
                                w_prob_exp=0.97)
+    # record the state entering every DDIM step and the noise drawn in it, so that parity tests can teacher-force
+    # single steps (whole-loop comparisons compound rounding differences by sqrt(1/abar - 1) ~ 1.8e3)
+    trace = {}
+    orig_mp = diff.model_predictions
+
+    def rec_mp(shape, x, t, *a, **k):
+        trace[f"x{len([q for q in trace if q.startswith('x')])}"] = x.detach().clone().numpy()
+        return orig_mp(shape, x, t, *a, **k)
+    diff.model_predictions = rec_mp
+    orig_rl = torch.randn_like
+
+    def rec_rl(t, **k):
+        n = orig_rl(t, **k)
+        trace[f"z{len([q for q in trace if q.startswith('z')])}"] = n.detach().clone().numpy()
+        return n
+    torch.randn_like = rec_rl
     torch.manual_seed(43)
     y = diff.sample(batch_size=B, design_fn=design_fn0, design_guidance="standard", init=init)
-    np.savez_compressed(os.path.join(HERE, "sampler_loop_ddim3.npz"), init=init.numpy(), y=y.numpy())
+    torch.randn_like = orig_rl
+    np.savez_compressed(os.path.join(HERE, "sampler_loop_ddim3.npz"), init=init.numpy(), y=y.numpy(), **trace)
     print("sampler loops done")
 
 

@@ -2,7 +2,7 @@
 plain fp32/fp64 PyTorch references of the same op on seeded inputs.  Tolerances:
   - elementwise / normalisation / attention (fp32 SIMT): 2e-5 relative to the output scale
   - TF32 tensor-core contractions: 3e-3 relative to the output scale (10-bit mantissa operands, fp32 accumulate)
-  - 3xTF32 contractions: 2e-5
+  - 3xTF32 contractions: 5e-5 (operand error ~2^-22; the rest is the tensor core's non-IEEE fp32 accumulation over K<=6912)
   - fused sampler step: bit-exact against the reference's recorded step (tests/golden/sampler_step_*.npz)
 """
 import os
@@ -20,6 +20,7 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 TOL_F32 = 2e-5
 TOL_TF32 = 3e-3
+TOL_3X = 5e-5
 
 
 def rel_err(a, b):
@@ -99,7 +100,7 @@ def test_conv3x3x3_bias_stats(case, precise):
     wp, _, _ = packing.pack_conv3d(w.to(DEV), tf32=not precise)
     y, stats, _ = run_conv(x1.to(DEV), wp, 27, x2=x2.to(DEV) if C2 else None, bias=bias.to(DEV), cout=Cout, pad=(1, 1, 1),
                            kernel=(3, 3, 3), gn_groups=groups, precise=precise)
-    assert rel_err(y, ref) <= (TOL_F32 if precise else TOL_TF32)
+    assert rel_err(y, ref) <= (TOL_3X if precise else TOL_TF32)
     # statistics are those of the values actually written
     v = y.double().reshape(B, -1, groups, Cout // groups)
     assert torch.allclose(stats[:, :, 0], v.sum(dim=(1, 3)), rtol=1e-6, atol=1e-6)
@@ -176,7 +177,7 @@ def test_linear_residual_and_reference_layout_output():
     w3 = torch.randn(384, 128, generator=gen) / 128 ** 0.5
     ref3 = x.double() @ w3.double().t()
     y3, _, _ = run_conv(x.to(DEV), packing.pack_linear(w3.to(DEV), tf32=False), 1, cout=384, precise=True)
-    assert rel_err(y3, ref3) <= TOL_F32
+    assert rel_err(y3, ref3) <= TOL_3X
 
 
 @pytest.mark.parametrize("with_ss,with_res", [(True, False), (False, True), (False, False)])

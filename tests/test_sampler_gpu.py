@@ -42,16 +42,28 @@ def test_ddpm_loop_matches_reference(golden_dir, monkeypatch):
     assert (y - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
 
 
-def test_ddim_loop_matches_reference(golden_dir, monkeypatch):
+def test_ddim_steps_match_reference_trace(golden_dir):
+    """Teacher-forced DDIM steps on the reference's recorded per-step states and noise (1000 -> 3 steps, eta = 1).
+    A DDIM step maps an eps perturbation d to  d * (sqrt(1/abar_t - 1) * sqrt(abar_next) + c): up to ~6e2 on this
+    schedule, so the bound is that amplification times the fp32-class U-Net tolerance (1e-4), plus 1e-5."""
+    from oracle import smoke_sampler_oracle as so
     z = np.load(os.path.join(golden_dir, "sampler_loop_ddim3.npz"))
     d = sampler(timesteps=1000, sampling_timesteps=3, ddim_sampling_eta=1.0, standard_fixed_ratio=1e5, coeff_ratio=0.0,
                 w_prob_exp=0.97)
-    cpu_noise(monkeypatch)
-    torch.manual_seed(43)
-    y = d.sample(batch_size=2, design_fn=dpc.StockSmokeGuidance(), design_guidance="standard",
-                 init=torch.from_numpy(z["init"])).cpu()
-    ref = torch.from_numpy(z["y"])
-    assert (y - ref).abs().max().item() <= 2e-3 * max(1.0, ref.abs().max().item())
+    sch = d._sched()
+    init = torch.from_numpy(z["init"]).cuda()
+    pairs = so.ddim_times(1000, 3)
+    for i, (time, time_next) in enumerate(pairs):
+        x = torch.from_numpy(z[f"x{i}"]).cuda()
+        last = time_next < 0
+        noise = None if last else torch.from_numpy(z[f"z{i}"]).cuda()
+        out = d.ddim_step(x, time, time_next, design_fn=dpc.StockSmokeGuidance(), design_guidance="standard", init=init,
+                          noise=noise).cpu()
+        ref = torch.from_numpy(z["y"] if last else z[f"x{i + 1}"])
+        srm1 = float(sch["sqrt_recipm1_alphas_cumprod"][time])
+        amp = srm1 if last else srm1 * float(sch["alphas_cumprod"][time_next].sqrt()) + 1.0
+        err = (out - ref).abs().max().item()
+        assert err <= 1e-4 * amp + 1e-5, (i, err, amp)
 
 
 def test_sampling_properties_tf32_mode():
