@@ -71,11 +71,12 @@ typedef struct dpc_conv_params {
 
 int dpc_conv_igemm(const dpc_conv_params* p, void* stream);
 
-/* 3x3x3 / pad 1 Conv3d on the 5th-generation tensor cores: TMA-tiled operand staging, tcgen05.mma (kind::tf32)
- * with the accumulator in TMEM.  Same arguments and epilogue as dpc_conv_igemm; requires ntaps == 27, unit stride,
- * C1 % 32 == 0, C2 % 32 == 0, Cout % 16 == 0, Cout <= 256, (Ho*Wo) % 128 == 0 or 128 % Wo == 0.
- * `w` must be packed [27][Cout][Cin] (tap-major, K contiguous).  Returns -2 if the shape is not supported so the
- * host mirror can fall back to dpc_conv_igemm (same numerics class). */
+/* 3x3x3 / pad 1 Conv3d on the 5th-generation tensor cores: TMA-tiled operand staging (one halo box per
+ * (dt, 32-channel chunk, dw) shared by the three dh taps), tcgen05.mma kind::tf32, accumulators in TMEM.
+ * Same arguments, weight packing and epilogue as dpc_conv_igemm.  Supported: ntaps == 27, unit stride, pad 1,
+ * channels-last output, no residual, C1 % 32 == 0, C2 % 32 == 0, Cout in {64,128,256} == Npad, W % 8 == 0, 128 % W == 0,
+ * 128/W <= H <= 256, gn_groups in {0, 8}.  Returns -2 (nothing launched) for any other shape so the host mirror can
+ * use dpc_conv_igemm (same numerics class). */
 int dpc_conv3d_tcgen05(const dpc_conv_params* p, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------

@@ -335,3 +335,39 @@ def test_fused_ddim_step_matches_oracle():
         out = torch.empty(B, Fr, 6, S, S, device=DEV)
         _lib.guided_step(True, x.to(DEV), ej.to(DEV), ew.to(DEV), nz.to(DEV), init.to(DEV), None, c, out, None, B, Fr, S, S)
         assert torch.equal(out.cpu(), ref), (time, (out.cpu() - ref).abs().max())
+
+
+TC_CASES = [
+    # name, B, F, H, W, C1, C2, Cout
+    ("w16_64", 2, 4, 16, 16, 64, 0, 64),
+    ("w64_64", 1, 3, 64, 64, 64, 0, 64),
+    ("w32_64_to_128", 2, 3, 32, 32, 64, 0, 128),
+    ("w32_concat_128", 1, 2, 32, 32, 128, 128, 128),
+    ("w16_256", 1, 3, 16, 16, 256, 0, 256),
+    ("w16_concat_512_to_128", 1, 2, 16, 16, 256, 256, 128),
+    ("partial_tile_h40", 1, 2, 40, 16, 64, 0, 64),
+    ("w64_128_to_64_concat", 1, 2, 64, 64, 64, 64, 64),
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
+def test_conv3d_tcgen05(case):
+    """The TMA/tcgen05 kernel against fp64 conv3d and against the generic tensor-core kernel (same numerics class)."""
+    _, B, Fr, H, W, C1, C2, Cout = case
+    gen = g(21)
+    x1 = torch.randn(B, Fr, H, W, C1, generator=gen)
+    x2 = torch.randn(B, Fr, H, W, C2, generator=gen) if C2 else None
+    w = torch.randn(Cout, C1 + C2, 3, 3, 3, generator=gen) / (27 * (C1 + C2)) ** 0.5
+    bias = torch.randn(Cout, generator=gen)
+    xin = torch.cat([x1, x2], -1) if C2 else x1
+    ref = F.conv3d(ncdhw(xin).double(), w.double(), bias.double(), padding=1).permute(0, 2, 3, 4, 1)
+    wp, _, _ = packing.pack_conv3d(w.to(DEV))
+    kw = dict(x2=x2.to(DEV) if C2 else None, bias=bias.to(DEV), cout=Cout, pad=(1, 1, 1), kernel=(3, 3, 3), gn_groups=8)
+    y, stats, ran_tc = run_conv(x1.to(DEV), wp, 27, tcgen05=True, **kw)
+    assert ran_tc, "shape should be served by the tcgen05 kernel"
+    assert rel_err(y, ref) <= TOL_TF32
+    y2, stats2, _ = run_conv(x1.to(DEV), wp, 27, tcgen05=False, **kw)
+    assert rel_err(y, y2) <= 2e-4        # both truncate the same TF32 operands; only the accumulation order differs
+    v = y.double().reshape(B, -1, 8, Cout // 8)
+    assert torch.allclose(stats[:, :, 0], v.sum(dim=(1, 3)), rtol=1e-6, atol=1e-6)
+    assert torch.allclose(stats[:, :, 1], (v * v).sum(dim=(1, 3)), rtol=1e-6, atol=1e-6)
