@@ -118,6 +118,51 @@ class LaunchCounter:
     count = 0
 
 
+class Profiler:
+    """Optional per-call CUDA-event timing of the launches issued through this binding (development aid):
+        with Profiler() as prof: net(x, t)  ->  prof.summary() = {label: (calls, total ms)}"""
+    active = None
+
+    def __init__(self):
+        self.events = []
+
+    def __enter__(self):
+        Profiler.active = self
+        return self
+
+    def __exit__(self, *a):
+        Profiler.active = None
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for label, e0, e1 in self.events:
+            n, t = out.get(label, (0, 0.0))
+            out[label] = (n + 1, t + e0.elapsed_time(e1))
+        return out
+
+
+def _timed(label):
+    def deco(fn):
+        def wrapper(*a, **k):
+            prof = Profiler.active
+            if prof is None:
+                return fn(*a, **k)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **k)
+            e1.record()
+            lab = label
+            if label == "conv":
+                p = a[0]
+                lab = f"conv[{'tc' if r else 'igemm'} taps={p.ntaps} cin={p.C1 + p.C2} cout={p.Cout} w={p.Wi}]"
+            prof.events.append((lab, e0, e1))
+            return r
+        return wrapper
+    return deco
+
+
+@_timed("conv")
 def conv(params: ConvParams, tcgen05: bool = False) -> bool:
     """Launch a convolution.  With tcgen05=True tries the TMA/tcgen05 kernel first; returns True if it ran.
     Falls back to the generic tensor-core implicit GEMM only on the documented 'shape not supported' code (-2)."""
@@ -134,6 +179,7 @@ def conv(params: ConvParams, tcgen05: bool = False) -> bool:
     return False
 
 
+@_timed("groupnorm_silu")
 def groupnorm_silu(y, stats, gamma, beta, scale_shift, ss_stride, ss_off, residual, out, B, rows_per_sample, Cn, groups,
                    eps=1e-5):
     check(lib().dpc_groupnorm_silu(ptr(y), ptr(stats), ptr(gamma), ptr(beta), ptr(scale_shift), ss_stride, ss_off,
@@ -142,45 +188,53 @@ def groupnorm_silu(y, stats, gamma, beta, scale_shift, ss_stride, ss_off, residu
     LaunchCounter.count += 1
 
 
+@_timed("layernorm_channels")
 def layernorm_channels(x, gamma, out, rows, Cn, eps=1e-5):
     check(lib().dpc_layernorm_channels(ptr(x), ptr(gamma), ptr(out), rows, Cn, eps, stream_ptr()),
           "dpc_layernorm_channels")
     LaunchCounter.count += 1
 
 
+@_timed("pack_input")
 def pack_input(x, out, B, F, Ctot, c0, Cin, H, W, Cpad):
     check(lib().dpc_pack_input(ptr(x), ptr(out), B, F, Ctot, c0, Cin, H, W, Cpad, stream_ptr()), "dpc_pack_input")
     LaunchCounter.count += 1
 
 
+@_timed("temporal_attention")
 def temporal_attention(qkv, rope_cos, rope_sin, pos_bias, out, B, F, HW, heads, use_rope=True):
     check(lib().dpc_temporal_attention(ptr(qkv), ptr(rope_cos), ptr(rope_sin), ptr(pos_bias), ptr(out), B, F, HW, heads,
                                        1 if use_rope else 0, stream_ptr()), "dpc_temporal_attention")
     LaunchCounter.count += 1
 
 
+@_timed("spatial_attention")
 def spatial_attention(qkv, out, BF, HW, heads):
     check(lib().dpc_spatial_attention(ptr(qkv), ptr(out), BF, HW, heads, stream_ptr()), "dpc_spatial_attention")
     LaunchCounter.count += 1
 
 
+@_timed("spatial_linear_attention")
 def spatial_linear_attention(qkv, ctx_ws, out, BF, HW, heads):
     check(lib().dpc_spatial_linear_attention(ptr(qkv), ptr(ctx_ws), ptr(out), BF, HW, heads, stream_ptr()),
           "dpc_spatial_linear_attention")
     LaunchCounter.count += 2
 
 
+@_timed("time_embed")
 def time_embed(t, freqs, w1, b1, w2, b2, hidden_ws, t_emb, B, dim):
     check(lib().dpc_time_embed(ptr(t), ptr(freqs), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(hidden_ws), ptr(t_emb), B, dim,
                                stream_ptr()), "dpc_time_embed")
     LaunchCounter.count += 2
 
 
+@_timed("time_proj")
 def time_proj(t_emb, W, bias, out, B, tdim, total):
     check(lib().dpc_time_proj(ptr(t_emb), ptr(W), ptr(bias), ptr(out), B, tdim, total, stream_ptr()), "dpc_time_proj")
     LaunchCounter.count += 1
 
 
+@_timed("guided_step")
 def guided_step(ddim, x, eps_joint, eps_w, noise, init, g, coefs: StepCoefs, x_out, x_start_out, B, F, H, W):
     fn = lib().dpc_ddim_guided_step if ddim else lib().dpc_ddpm_guided_step
     check(fn(ptr(x), ptr(eps_joint), ptr(eps_w), ptr(noise), ptr(init), ptr(g), 1 if g is None else 0, C.byref(coefs),
@@ -188,6 +242,7 @@ def guided_step(ddim, x, eps_joint, eps_w, noise, init, g, coefs: StepCoefs, x_o
     LaunchCounter.count += 1
 
 
+@_timed("predict_x_start")
 def predict_x_start(x, eps, sr, srm1, clip, out):
     check(lib().dpc_predict_x_start(ptr(x), ptr(eps), sr, srm1, 1 if clip else 0, ptr(out), x.numel(), stream_ptr()),
           "dpc_predict_x_start")
