@@ -86,15 +86,17 @@ temporal_attention_kernel(const float* __restrict__ qkv, const float* __restrict
 #pragma unroll
         for (int j = 0; j < 32 * R; ++j) {
           if (j < F) {
-            float acc = 0.f;
+            // four independent partial sums: a 32-long dependent FMA chain would expose the 4-cycle FMA latency
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
             for (int c = 0; c < DH; c += 4) {
               float4 k4 = *reinterpret_cast<const float4*>(Ks + j * LD + c);
-              acc = fmaf(q[r][c], k4.x, acc);
-              acc = fmaf(q[r][c + 1], k4.y, acc);
-              acc = fmaf(q[r][c + 2], k4.z, acc);
-              acc = fmaf(q[r][c + 3], k4.w, acc);
+              a0 = fmaf(q[r][c], k4.x, a0);
+              a1 = fmaf(q[r][c + 1], k4.y, a1);
+              a2 = fmaf(q[r][c + 2], k4.z, a2);
+              a3 = fmaf(q[r][c + 3], k4.w, a3);
             }
+            float acc = (a0 + a1) + (a2 + a3);
             if (brow) acc += __ldg(brow + j);
             s[j] = acc;
             mx = fmaxf(mx, acc);
