@@ -1,14 +1,17 @@
 // 3x3x3 / pad 1 Conv3d (Block.proj, conv3d.py:189-204) on the 5th-generation tensor cores of sm_100a.
 //
 // Formulation: implicit GEMM, M = output voxels, N = Cout, K = 27 taps x Cin, TF32 operands, fp32 accumulate in TMEM.
-// The implicit-GEMM A operand re-reads every input voxel 27 times; fed tap-by-tap from L2 this kernel would be bound by
-// the ~42 B/clk/SM L2->SM path, not by the tensor pipe.  So one CTA owns a tall tile (S x 128 voxels = Hblk full image
-// rows of one frame, S accumulators side by side in TMEM) and stages, per (dt, 32-channel chunk, dw), ONE TMA box
-//       [32 ch] x [W] x [Hblk + 2 rows]          (start (w, h) = (dw-1, h0-1); out-of-bounds = zero fill = conv padding)
-// into 128B-swizzled shared memory.  The three dh taps and the S accumulators all read that box through UMMA descriptors
-// whose start address is shifted by whole image rows (W x 128 B, a multiple of the 1024 B swizzle atom), so the A
-// traffic per tile drops from 27 to 3(Hblk+2)/Hblk box-equivalents; weights ([Cout] x [32] K-major boxes per tap) are
-// amortised over the S accumulators.
+// The implicit-GEMM A operand re-reads every input voxel 27 times; fed tap-by-tap from L2 this kernel is bound by the
+// L2->SM path (measured: ~33 B/clk/SM), not by the tensor pipe.  So the nine in-plane taps share ONE shared-memory copy:
+//   * per (dt, 32-channel chunk) a single TMA box  [32 ch] x [W+2] x [R rows]  (start (w,h) = (-1, hq-1); out-of-bounds
+//     elements are zero-filled by TMA = the conv padding) lands in 128B-swizzled smem as rows of 128 B with pitch W+2;
+//   * outputs are enumerated in the same padded-flat order  mu = ho*(W+2) + wo  (the two pad columns per image row are
+//     computed and discarded: 3% at W=64), so tap (dh,dw) of the whole 128-row MMA operand is the SAME buffer shifted
+//     by dh*(W+2)+dw rows.  The UMMA descriptor start address may be any multiple of 128 B: the 128B swizzle is a
+//     function of the absolute smem address (verified on B200 with tools/umma_shift_probe.cu), no base_offset needed;
+//   * one CTA owns up to S=4 consecutive 128-row sub-tiles (S accumulators side by side in TMEM), so each weight box
+//     ([Cout] x [32], K-major) is amortised over S MMA groups.
+// A traffic per tile drops from 27 box-equivalents to ~3.4; the kernel becomes tensor-pipe bound for Cout >= 64.
 //
 // Warp roles (256 threads): warp 0 = TMA producer (one elected lane), warp 1 = tcgen05.mma issuer (one lane),
 // warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> +bias -> GroupNorm partial statistics -> global store).
@@ -32,7 +35,7 @@ struct Params {
   double* gn_stats;
   int B, F, H, W;
   int C1, C2, Cout;
-  int S, Hsub, Hblk, tiles_h;
+  int S, pitch, R, tiles_f;   // sub-tiles per CTA, smem row pitch (W+2), box rows, tiles per frame
   int NB;
   int a_bytes, b_bytes;
   int gn_groups;
@@ -127,10 +130,14 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x;
-  const int ht = tile % p.tiles_h;
-  const int f = (tile / p.tiles_h) % p.F;
-  const int b = tile / (p.tiles_h * p.F);
-  const int h0 = ht * p.Hblk;
+  const int tf = tile % p.tiles_f;
+  const int f = (tile / p.tiles_f) % p.F;
+  const int b = tile / (p.tiles_f * p.F);
+  const int mu_tile = tf * p.S * 128;                 // first padded-flat output position of this tile
+  const int hq = mu_tile / p.pitch;                   // image row of that position
+  const int mu0 = mu_tile - hq * p.pitch;             // its offset inside the row
+  const int npos = p.H * p.pitch - mu_tile;           // positions left in the frame
+  const int nsub = (npos >= p.S * 128) ? p.S : (npos + 127) / 128;
   const int Cin = p.C1 + p.C2;
   const int nch = Cin / KCH, nch1 = p.C1 / KCH;
   const int tmem_cols = (p.S * N <= 32) ? 32 : (p.S * N <= 64) ? 64 : (p.S * N <= 128) ? 128 : (p.S * N <= 256) ? 256 : 512;
@@ -163,20 +170,17 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       for (int ch = 0; ch < nch; ++ch) {
         const CUtensorMap* mp = (ch < nch1) ? &tmA1 : &tmA2;
         const int c0 = (ch < nch1) ? ch * KCH : (ch - nch1) * KCH;
-        for (int dw = 0; dw < 3; ++dw) {
-          const int sa = ia % NA;
-          mbar_wait(emptyA + 8 * sa, ((ia / NA) & 1) ^ 1);
-          mbar_expect_tx(fullA + 8 * sa, (uint32_t)p.a_bytes);
-          tma_load_5d(a_buf + sa * p.a_bytes, mp, fullA + 8 * sa, c0, dw - 1, h0 - 1, fz, b);
-          ++ia;
-          for (int dh = 0; dh < 3; ++dh) {
-            const int sb = ib % p.NB;
-            mbar_wait(emptyB + 8 * sb, ((ib / p.NB) & 1) ^ 1);
-            mbar_expect_tx(fullB + 8 * sb, (uint32_t)p.b_bytes);
-            const int tap = (dt * 3 + dh) * 3 + dw;
-            tma_load_2d(b_buf + sb * p.b_bytes, &tmW, fullB + 8 * sb, tap * Cin + ch * KCH, 0);
-            ++ib;
-          }
+        const int sa = ia % NA;
+        mbar_wait(emptyA + 8 * sa, ((ia / NA) & 1) ^ 1);
+        mbar_expect_tx(fullA + 8 * sa, (uint32_t)(p.R * p.pitch * ROW_BYTES));
+        tma_load_5d(a_buf + sa * p.a_bytes, mp, fullA + 8 * sa, c0, -1, hq - 1, fz, b);
+        ++ia;
+        for (int t9 = 0; t9 < 9; ++t9) {
+          const int sb = ib % p.NB;
+          mbar_wait(emptyB + 8 * sb, ((ib / p.NB) & 1) ^ 1);
+          mbar_expect_tx(fullB + 8 * sb, (uint32_t)p.b_bytes);
+          tma_load_2d(b_buf + sb * p.b_bytes, &tmW, fullB + 8 * sb, (dt * 9 + t9) * Cin + ch * KCH, 0);
+          ++ib;
         }
       }
     }
@@ -184,36 +188,34 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     // ------------------------------------------- MMA issuer ---------------------------------------------
     // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    const uint32_t sub_bytes = (uint32_t)(p.Hsub * p.W * ROW_BYTES);   // one 128-voxel sub-tile of the box
-    const uint32_t row_bytes = (uint32_t)(p.W * ROW_BYTES);            // one image row (dh shift)
     int ia = 0, ib = 0;
     uint32_t first = 0;                                                // becomes 1 after the first K block
     for (int dt = 0; dt < 3; ++dt) {
       for (int ch = 0; ch < nch; ++ch) {
-        for (int dw = 0; dw < 3; ++dw) {
-          const int sa = ia % NA;
-          mbar_wait(fullA + 8 * sa, (ia / NA) & 1);
+        const int sa = ia % NA;
+        mbar_wait(fullA + 8 * sa, (ia / NA) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a0 = a_buf + sa * p.a_bytes + (uint32_t)(mu0 * ROW_BYTES);
+        for (int t9 = 0; t9 < 9; ++t9) {
+          const int dh = t9 / 3, dw = t9 - dh * 3;
+          const int sb = ib % p.NB;
+          mbar_wait(fullB + 8 * sb, (ib / p.NB) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a0 = a_buf + sa * p.a_bytes;
-          for (int dh = 0; dh < 3; ++dh) {
-            const int sb = ib % p.NB;
-            mbar_wait(fullB + 8 * sb, (ib / p.NB) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t b0 = b_buf + sb * p.b_bytes;
-            for (int s = 0; s < p.S; ++s) {
-              const uint32_t a_s = a0 + s * sub_bytes + dh * row_bytes;
+          const uint32_t b0 = b_buf + sb * p.b_bytes;
+          const uint32_t a_tap = a0 + (uint32_t)((dh * p.pitch + dw) * ROW_BYTES);
+          for (int s = 0; s < nsub; ++s) {
+            const uint32_t a_s = a_tap + (uint32_t)(s * 128 * ROW_BYTES);
 #pragma unroll
-              for (int k = 0; k < KCH / 8; ++k)
-                umma_tf32(tmem_base + (uint32_t)(s * N), umma_desc(a_s + k * 32), umma_desc(b0 + k * 32), idesc,
-                          first | (uint32_t)k);
-            }
-            first = 1;
-            umma_commit(emptyB + 8 * sb);     // weights slot free once these MMAs retire
-            ++ib;
+            for (int k = 0; k < KCH / 8; ++k)
+              umma_tf32(tmem_base + (uint32_t)(s * N), umma_desc(a_s + k * 32), umma_desc(b0 + k * 32), idesc,
+                        first | (uint32_t)k);
           }
-          umma_commit(emptyA + 8 * sa);
-          ++ia;
+          first = 1;
+          umma_commit(emptyB + 8 * sb);     // weights slot free once these MMAs retire
+          ++ib;
         }
+        umma_commit(emptyA + 8 * sa);
+        ++ia;
       }
     }
     umma_commit(accum_bar);
@@ -229,11 +231,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     double gs[8], gq[8];
 #pragma unroll
     for (int g = 0; g < 8; ++g) gs[g] = gq[g] = 0.0;
-    for (int s = 0; s < p.S; ++s) {
-      const int r = s * 128 + q * 32 + lane;      // voxel index inside the tile
-      const int hl = r / p.W, w = r - hl * p.W;
-      const int h = h0 + hl;
-      const bool valid = h < p.H;
+    for (int s = 0; s < nsub; ++s) {
+      const int mu = mu_tile + s * 128 + q * 32 + lane;   // padded-flat output position inside the frame
+      const int h = mu / p.pitch, w = mu - h * p.pitch;
+      const bool valid = (h < p.H) && (w < p.W);
       const size_t m = (((size_t)b * p.F + f) * p.H + h) * p.W + w;
       float* dst = p.y + m * N;
 #pragma unroll
@@ -315,12 +316,12 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-static int make_act_map(CUtensorMap* m, const float* x, int B, int F, int H, int W, int C, int box_h) {
+static int make_act_map(CUtensorMap* m, const float* x, int B, int F, int H, int W, int C, int box_w, int box_h) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_err(-1, "cuTensorMapEncodeTiled unavailable", __FILE__, __LINE__);
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)F, (cuuint64_t)B};
   cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4, (cuuint64_t)F * H * W * C * 4};
-  cuuint32_t box[5] = {(cuuint32_t)KCH, (cuuint32_t)W, (cuuint32_t)box_h, 1, 1};
+  cuuint32_t box[5] = {(cuuint32_t)KCH, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -349,7 +350,7 @@ static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMa
     DPC_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  const unsigned grid = (unsigned)((size_t)p.B * p.F * p.tiles_h);
+  const unsigned grid = (unsigned)((size_t)p.B * p.F * p.tiles_f);
   conv3d_tc_kernel<N><<<grid, 256, smem, st>>>(a1, a2, wm, p);
   DPC_LAUNCH_CHECK();
   return 0;
@@ -369,38 +370,38 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
       c.ntaps == 27 && c.st == 1 && c.sh == 1 && c.sw == 1 && c.pt == 1 && c.ph == 1 && c.pw == 1 && c.Fo == F &&
       c.Ho == H && c.Wo == W && c.oh_mul == 1 && c.ow_mul == 1 && c.Hfull == H && c.Wfull == W && c.out_layout == 0 &&
       c.residual == nullptr && c.precise == 0 && c.C1 % KCH == 0 && c.C2 % KCH == 0 && c.C1 > 0 &&
-      (c.Cout == 64 || c.Cout == 128 || c.Cout == 256) && c.Npad == c.Cout && W % 8 == 0 && W <= 128 && 128 % W == 0 &&
-      (128 / W) <= H && H <= 256 && c.Kpad == 27 * (c.C1 + c.C2);
+      (c.Cout == 64 || c.Cout == 128 || c.Cout == 256) && c.Npad == c.Cout && W >= 2 && W + 2 <= 256 && H >= 1 &&
+      c.Kpad == 27 * (c.C1 + c.C2);
   if (!shape_ok) return -2;
   if (c.gn_stats && c.gn_groups != 8) return -2;   // the epilogue is specialised for GroupNorm(8), the reference default
   DPC_CHECK_ARG(c.x1 && c.w && c.y && (c.C2 == 0 || c.x2));
   Params p;
   p.bias = c.bias; p.y = c.y; p.gn_stats = c.gn_stats; p.gn_groups = c.gn_groups;
   p.B = c.B; p.F = F; p.H = H; p.W = W; p.C1 = c.C1; p.C2 = c.C2; p.Cout = c.Cout;
-  p.Hsub = 128 / W;
-  const int nsub_frame = (H + p.Hsub - 1) / p.Hsub;
+  p.pitch = W + 2;
+  const int frame_pos = H * p.pitch;
   int S = 512 / c.Cout;
   if (S > MAXS) S = MAXS;
-  if (S > nsub_frame) S = nsub_frame;
+  if (S > (frame_pos + 127) / 128) S = (frame_pos + 127) / 128;
   const size_t budget = 227 * 1024 - 2048;
   p.b_bytes = c.Cout * ROW_BYTES;
   for (;; --S) {
-    p.a_bytes = (S * p.Hsub + 2) * W * ROW_BYTES;
+    p.R = (p.pitch - 1 + S * 128 + 2 * p.pitch + 2 + p.pitch - 1) / p.pitch;
+    p.a_bytes = ((p.R * p.pitch * ROW_BYTES + 1023) / 1024) * 1024;
     if ((size_t)NA * p.a_bytes + 3 * (size_t)p.b_bytes + 1024 + 256 <= budget || S == 1) break;
   }
-  if ((size_t)NA * p.a_bytes + 3 * (size_t)p.b_bytes + 1024 + 256 > budget) return -2;
+  if ((size_t)NA * p.a_bytes + 3 * (size_t)p.b_bytes + 1024 + 256 > budget || p.R > 256) return -2;
   p.S = S;
-  p.Hblk = S * p.Hsub;
-  p.tiles_h = (H + p.Hblk - 1) / p.Hblk;
+  p.tiles_f = (frame_pos + S * 128 - 1) / (S * 128);
   int NB = (int)((budget - 1024 - 256 - (size_t)NA * p.a_bytes) / p.b_bytes);
-  if (NB > 8) NB = 8;
+  if (NB > 9) NB = 9;
   p.NB = NB;
   const size_t smem = (size_t)NA * p.a_bytes + (size_t)NB * p.b_bytes + 1024 + 256;
   CUtensorMap a1, a2, wm;
-  int rc = make_act_map(&a1, c.x1, c.B, F, H, W, c.C1, p.Hblk + 2);
+  int rc = make_act_map(&a1, c.x1, c.B, F, H, W, c.C1, p.pitch, p.R);
   if (rc) return rc;
   if (c.C2) {
-    rc = make_act_map(&a2, c.x2, c.B, F, H, W, c.C2, p.Hblk + 2);
+    rc = make_act_map(&a2, c.x2, c.B, F, H, W, c.C2, p.pitch, p.R);
     if (rc) return rc;
   } else {
     a2 = a1;

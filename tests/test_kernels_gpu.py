@@ -347,6 +347,9 @@ TC_CASES = [
     ("w16_concat_512_to_128", 1, 2, 16, 16, 256, 256, 128),
     ("partial_tile_h40", 1, 2, 40, 16, 64, 0, 64),
     ("w64_128_to_64_concat", 1, 2, 64, 64, 64, 64, 64),
+    ("w8_128", 2, 4, 8, 8, 128, 0, 128),
+    ("w4_256", 1, 6, 4, 4, 256, 0, 256),
+    ("nonsquare_h12_w20", 2, 3, 12, 20, 64, 0, 64),
 ]
 
 
