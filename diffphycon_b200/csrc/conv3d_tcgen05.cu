@@ -98,6 +98,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t adesc, uint6
       ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -184,8 +189,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         }
       }
     }
-  } else if (warp == 1 && lane == 0) {
+  } else if (warp == 1) {
     // ------------------------------------------- MMA issuer ---------------------------------------------
+    // The whole warp walks the pipeline (warp-uniform control flow keeps descriptors in uniform registers); one
+    // elected lane issues.  Descriptors are advanced by integer adds on the 16-byte-unit start-address field:
+    // +2 per K=8 step (32 B), +1024 per 128-row sub-tile, +(dh*pitch+dw)*8 per tap.
     // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     int ia = 0, ib = 0;
@@ -195,30 +203,37 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         const int sa = ia % NA;
         mbar_wait(fullA + 8 * sa, (ia / NA) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a0 = a_buf + sa * p.a_bytes + (uint32_t)(mu0 * ROW_BYTES);
+        const uint64_t adesc0 = umma_desc(a_buf + sa * p.a_bytes + (uint32_t)(mu0 * ROW_BYTES));
         for (int t9 = 0; t9 < 9; ++t9) {
           const int dh = t9 / 3, dw = t9 - dh * 3;
           const int sb = ib % p.NB;
           mbar_wait(fullB + 8 * sb, (ib / p.NB) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t b0 = b_buf + sb * p.b_bytes;
-          const uint32_t a_tap = a0 + (uint32_t)((dh * p.pitch + dw) * ROW_BYTES);
-          for (int s = 0; s < nsub; ++s) {
-            const uint32_t a_s = a_tap + (uint32_t)(s * 128 * ROW_BYTES);
+          const uint64_t bdesc = umma_desc(b_buf + sb * p.b_bytes);
+          const uint64_t adesc = adesc0 + (uint64_t)((dh * p.pitch + dw) * (ROW_BYTES / 16));
+          if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < KCH / 8; ++k)
-              umma_tf32(tmem_base + (uint32_t)(s * N), umma_desc(a_s + k * 32), umma_desc(b0 + k * 32), idesc,
-                        first | (uint32_t)k);
+            for (int s = 0; s < MAXS; ++s) {
+              if (s < nsub) {
+#pragma unroll
+                for (int k = 0; k < KCH / 8; ++k)
+                  umma_tf32(tmem_base + (uint32_t)(s * N), adesc + (uint64_t)(s * (128 * ROW_BYTES / 16) + 2 * k),
+                            bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
+              }
+            }
+            umma_commit(emptyB + 8 * sb);     // weights slot free once these MMAs retire
           }
+          __syncwarp();
           first = 1;
-          umma_commit(emptyB + 8 * sb);     // weights slot free once these MMAs retire
           ++ib;
         }
-        umma_commit(emptyA + 8 * sa);
+        if (elect_one()) umma_commit(emptyA + 8 * sa);
+        __syncwarp();
         ++ia;
       }
     }
-    umma_commit(accum_bar);
+    if (elect_one()) umma_commit(accum_bar);
+    __syncwarp();
   } else if (warp >= 4) {
     // ------------------------------------------- epilogue -----------------------------------------------
     const int q = warp - 4;                       // TMEM lane quarter == warp_id % 4
