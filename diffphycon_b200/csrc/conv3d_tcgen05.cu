@@ -28,6 +28,7 @@ constexpr int KCH = 32;            // channels per K block: 32 fp32 = one 128-by
 constexpr int ROW_BYTES = 128;
 constexpr int NA = 2;              // A ring depth
 constexpr int MAXS = 4;
+constexpr int APARTS = 3;           // the A box of a block is fetched as APARTS row slabs
 
 struct Params {
   const float* bias;
@@ -120,6 +121,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 template <int N>
 __global__ void __launch_bounds__(256, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                 const __grid_constant__ CUtensorMap tmA1t, const __grid_constant__ CUtensorMap tmA2t,
                  const __grid_constant__ CUtensorMap tmW, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -169,25 +171,40 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
 
   if (warp == 0 && lane == 0) {
     // ------------------------------------------- TMA producer -------------------------------------------
-    int ia = 0, ib = 0;
-    for (int dt = 0; dt < 3; ++dt) {
-      const int fz = f + dt - 1;
-      for (int ch = 0; ch < nch; ++ch) {
-        const CUtensorMap* mp = (ch < nch1) ? &tmA1 : &tmA2;
-        const int c0 = (ch < nch1) ? ch * KCH : (ch - nch1) * KCH;
-        const int sa = ia % NA;
-        mbar_wait(emptyA + 8 * sa, ((ia / NA) & 1) ^ 1);
+    // Issue order follows slot availability: the weight boxes of block j that fit the ring go first, then the A box of
+    // block j+1 (its buffer frees when block j-1 retires) cut into APARTS row slabs interleaved with the remaining
+    // weight boxes, so a 90 KB A transfer never sits in front of a weight box the tensor pipe is about to need.
+    const int nblk = 3 * nch;
+    const int rows_part = (p.R + APARTS - 1) / APARTS;
+    auto issue_a_part = [&](int j, int part) {
+      const int dt = j / nch, ch = j - dt * nch;
+      const CUtensorMap* mp = (ch < nch1) ? &tmA1 : &tmA2;
+      const int c0 = (ch < nch1) ? ch * KCH : (ch - nch1) * KCH;
+      const int sa = j % NA;
+      const int r0 = part * rows_part;
+      if (r0 >= p.R) return;
+      if (part == 0) {
+        mbar_wait(emptyA + 8 * sa, ((j / NA) & 1) ^ 1);
         mbar_expect_tx(fullA + 8 * sa, (uint32_t)(p.R * p.pitch * ROW_BYTES));
-        tma_load_5d(a_buf + sa * p.a_bytes, mp, fullA + 8 * sa, c0, -1, hq - 1, fz, b);
-        ++ia;
-        for (int t9 = 0; t9 < 9; ++t9) {
-          const int sb = ib % p.NB;
-          mbar_wait(emptyB + 8 * sb, ((ib / p.NB) & 1) ^ 1);
-          mbar_expect_tx(fullB + 8 * sb, (uint32_t)p.b_bytes);
-          tma_load_2d(b_buf + sb * p.b_bytes, &tmW, fullB + 8 * sb, (dt * 9 + t9) * Cin + ch * KCH, 0);
-          ++ib;
-        }
       }
+      const CUtensorMap* mpp = (r0 + rows_part <= p.R) ? mp : ((ch < nch1) ? &tmA1t : &tmA2t);
+      tma_load_5d(a_buf + sa * p.a_bytes + (uint32_t)(r0 * p.pitch * ROW_BYTES), mpp, fullA + 8 * sa, c0, -1,
+                  hq - 1 + r0, f + dt - 1, b);
+    };
+    int ib = 0;
+    for (int part = 0; part < APARTS; ++part) issue_a_part(0, part);
+    for (int j = 0; j < nblk; ++j) {
+      const int dt = j / nch, ch = j - dt * nch;
+      int next_part = 0;
+      for (int t9 = 0; t9 < 9; ++t9) {
+        const int sb = ib % p.NB;
+        mbar_wait(emptyB + 8 * sb, ((ib / p.NB) & 1) ^ 1);
+        mbar_expect_tx(fullB + 8 * sb, (uint32_t)p.b_bytes);
+        tma_load_2d(b_buf + sb * p.b_bytes, &tmW, fullB + 8 * sb, (dt * 9 + t9) * Cin + ch * KCH, 0);
+        ++ib;
+        if (j + 1 < nblk && t9 + 1 >= p.NB - 1 && next_part < APARTS) issue_a_part(j + 1, next_part++);
+      }
+      while (j + 1 < nblk && next_part < APARTS) issue_a_part(j + 1, next_part++);
     }
   } else if (warp == 1) {
     // ------------------------------------------- MMA issuer ---------------------------------------------
@@ -358,15 +375,15 @@ static int make_w_map(CUtensorMap* m, const float* w, int Kpad, int Npad, int N)
 }
 
 template <int N>
-static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& wm, const Params& p, size_t smem,
-                  cudaStream_t st) {
+static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& a1t, const CUtensorMap& a2t,
+                  const CUtensorMap& wm, const Params& p, size_t smem, cudaStream_t st) {
   static size_t configured = 0;
   if (smem > configured) {
     DPC_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
   const unsigned grid = (unsigned)((size_t)p.B * p.F * p.tiles_f);
-  conv3d_tc_kernel<N><<<grid, 256, smem, st>>>(a1, a2, wm, p);
+  conv3d_tc_kernel<N><<<grid, 256, smem, st>>>(a1, a2, a1t, a2t, wm, p);
   DPC_LAUNCH_CHECK();
   return 0;
 }
@@ -412,19 +429,28 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   if (NB > 9) NB = 9;
   p.NB = NB;
   const size_t smem = (size_t)NA * p.a_bytes + (size_t)NB * p.b_bytes + 1024 + 256;
-  CUtensorMap a1, a2, wm;
-  int rc = make_act_map(&a1, c.x1, c.B, F, H, W, c.C1, p.pitch, p.R);
+  // the A box is fetched as APARTS slabs of rows_part rows; the last slab may be shorter -> its own tensor map
+  const int rows_part = (p.R + APARTS - 1) / APARTS;
+  const int nfull = p.R / rows_part;
+  const int tail_rows = p.R - nfull * rows_part;
+  CUtensorMap a1, a2, a1t, a2t, wm;
+  int rc = make_act_map(&a1, c.x1, c.B, F, H, W, c.C1, p.pitch, rows_part);
+  if (rc) return rc;
+  rc = make_act_map(&a1t, c.x1, c.B, F, H, W, c.C1, p.pitch, tail_rows > 0 ? tail_rows : rows_part);
   if (rc) return rc;
   if (c.C2) {
-    rc = make_act_map(&a2, c.x2, c.B, F, H, W, c.C2, p.pitch, p.R);
+    rc = make_act_map(&a2, c.x2, c.B, F, H, W, c.C2, p.pitch, rows_part);
+    if (rc) return rc;
+    rc = make_act_map(&a2t, c.x2, c.B, F, H, W, c.C2, p.pitch, tail_rows > 0 ? tail_rows : rows_part);
     if (rc) return rc;
   } else {
     a2 = a1;
+    a2t = a1t;
   }
   rc = make_w_map(&wm, c.w, c.Kpad, c.Npad, c.Cout);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (c.Cout == 64) return launch<64>(a1, a2, wm, p, smem, st);
-  if (c.Cout == 128) return launch<128>(a1, a2, wm, p, smem, st);
-  return launch<256>(a1, a2, wm, p, smem, st);
+  if (c.Cout == 64) return launch<64>(a1, a2, a1t, a2t, wm, p, smem, st);
+  if (c.Cout == 128) return launch<128>(a1, a2, a1t, a2t, wm, p, smem, st);
+  return launch<256>(a1, a2, a1t, a2t, wm, p, smem, st);
 }
