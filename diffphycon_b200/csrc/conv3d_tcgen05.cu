@@ -20,6 +20,7 @@
 #include "common.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace dpc {
 namespace tc {
@@ -40,6 +41,7 @@ struct Params {
   int NB;
   int a_bytes, b_bytes;
   int gn_groups;
+  int debug;   // development switches (env DPC_TC_DEBUG): 1 = no MMA issue, 2 = no TMA loads/waits, 4 = no epilogue stores
 };
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -169,7 +171,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && lane == 0 && !(p.debug & 2)) {
     // ------------------------------------------- TMA producer -------------------------------------------
     // Issue order follows slot availability: the weight boxes of block j that fit the ring go first, then the A box of
     // block j+1 (its buffer frees when block j-1 retires) cut into APARTS row slabs interleaved with the remaining
@@ -218,20 +220,20 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     for (int dt = 0; dt < 3; ++dt) {
       for (int ch = 0; ch < nch; ++ch) {
         const int sa = ia % NA;
-        mbar_wait(fullA + 8 * sa, (ia / NA) & 1);
+        if (!(p.debug & 2)) mbar_wait(fullA + 8 * sa, (ia / NA) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint64_t adesc0 = umma_desc(a_buf + sa * p.a_bytes + (uint32_t)(mu0 * ROW_BYTES));
         for (int t9 = 0; t9 < 9; ++t9) {
           const int dh = t9 / 3, dw = t9 - dh * 3;
           const int sb = ib % p.NB;
-          mbar_wait(fullB + 8 * sb, (ib / p.NB) & 1);
+          if (!(p.debug & 2)) mbar_wait(fullB + 8 * sb, (ib / p.NB) & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t bdesc = umma_desc(b_buf + sb * p.b_bytes);
           const uint64_t adesc = adesc0 + (uint64_t)((dh * p.pitch + dw) * (ROW_BYTES / 16));
           if (elect_one()) {
 #pragma unroll
             for (int s = 0; s < MAXS; ++s) {
-              if (s < nsub) {
+              if (s < nsub && !(p.debug & 1)) {
 #pragma unroll
                 for (int k = 0; k < KCH / 8; ++k)
                   umma_tf32(tmem_base + (uint32_t)(s * N), adesc + (uint64_t)(s * (128 * ROW_BYTES / 16) + 2 * k),
@@ -284,7 +286,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           o[j + 2] = __uint_as_float(v[j + 2]) + bv.z;
           o[j + 3] = __uint_as_float(v[j + 3]) + bv.w;
         }
-        if (valid) {
+        if (valid && !(p.debug & 4)) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<float4*>(dst + c * 32 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
@@ -409,6 +411,7 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   DPC_CHECK_ARG(c.x1 && c.w && c.y && (c.C2 == 0 || c.x2));
   Params p;
   p.bias = c.bias; p.y = c.y; p.gn_stats = c.gn_stats; p.gn_groups = c.gn_groups;
+  { const char* e = getenv("DPC_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
   p.B = c.B; p.F = F; p.H = H; p.W = W; p.C1 = c.C1; p.C2 = c.C2; p.Cout = c.Cout;
   p.pitch = W + 2;
   const int frame_pos = H * p.pitch;
