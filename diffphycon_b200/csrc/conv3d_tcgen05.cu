@@ -120,6 +120,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
 }
 
+__device__ long long g_tc_ts[16];   // development timestamps of one CTA (debug & 8)
+#define TS(i) do { if ((p.debug & 8) && blockIdx.x == 1000) g_tc_ts[i] = clock64(); } while (0)
+
 template <int N>
 __global__ void __launch_bounds__(256, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
@@ -138,6 +141,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   __shared__ double s_stat[2][8];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TS(0);
   const int tile = blockIdx.x;
   const int tf = tile % p.tiles_f;
   const int f = (tile / p.tiles_f) % p.F;
@@ -170,6 +174,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (threadIdx.x == 0) TS(1);
 
   if (warp == 0 && lane == 0 && !(p.debug & 2)) {
     // ------------------------------------------- TMA producer -------------------------------------------
@@ -222,6 +227,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         const int sa = ia % NA;
         if (!(p.debug & 2)) mbar_wait(fullA + 8 * sa, (ia / NA) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (ia == 0 && lane == 0) TS(2);
         const uint64_t adesc0 = umma_desc(a_buf + sa * p.a_bytes + (uint32_t)(mu0 * ROW_BYTES));
         for (int t9 = 0; t9 < 9; ++t9) {
           const int dh = t9 / 3, dw = t9 - dh * 3;
@@ -253,11 +259,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     }
     if (elect_one()) umma_commit(accum_bar);
     __syncwarp();
+    if (lane == 0) TS(3);
   } else if (warp >= 4) {
     // ------------------------------------------- epilogue -----------------------------------------------
     const int q = warp - 4;                       // TMEM lane quarter == warp_id % 4
     mbar_wait(accum_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (threadIdx.x == 128) TS(4);
     const bool do_stats = p.gn_stats != nullptr;
     // GroupNorm(8): group width N/8 columns, GPC groups per 32-column chunk; one (sum, sumsq) pair per group
     constexpr int GPC = 256 / N;        // 4, 2, 1 for N = 64, 128, 256
@@ -306,6 +314,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         }
       }
     }
+    if (threadIdx.x == 128) TS(5);
     if (do_stats) {
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
@@ -326,8 +335,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       }
     }
   }
+  if (threadIdx.x == 128) TS(6);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (threadIdx.x == 0) TS(7);
   if (warp == 2) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
@@ -456,4 +467,11 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   if (c.Cout == 64) return launch<64>(a1, a2, a1t, a2t, wm, p, smem, st);
   if (c.Cout == 128) return launch<128>(a1, a2, a1t, a2t, wm, p, smem, st);
   return launch<256>(a1, a2, a1t, a2t, wm, p, smem, st);
+}
+
+extern "C" int dpc_tc_debug_timestamps(long long* out16) {
+  using namespace dpc;
+  DPC_CUDA(cudaDeviceSynchronize());
+  DPC_CUDA(cudaMemcpyFromSymbol(out16, dpc::tc::g_tc_ts, sizeof(long long) * 16));
+  return 0;
 }
