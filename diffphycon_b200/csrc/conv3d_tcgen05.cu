@@ -233,10 +233,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           const int dh = t9 / 3, dw = t9 - dh * 3;
           const int sb = ib % p.NB;
           if (!(p.debug & 2)) mbar_wait(fullB + 8 * sb, (ib / p.NB) & 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (!(p.debug & 32)) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint64_t bdesc = umma_desc(b_buf + sb * p.b_bytes);
           const uint64_t adesc = adesc0 + (uint64_t)((dh * p.pitch + dw) * (ROW_BYTES / 16));
-          if (elect_one()) {
+          if ((p.debug & 64) ? (lane == 0) : elect_one()) {
 #pragma unroll
             for (int s = 0; s < MAXS; ++s) {
               if (s < nsub && !(p.debug & 1)) {
@@ -246,7 +246,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
                             bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
               }
             }
-            umma_commit(emptyB + 8 * sb);     // weights slot free once these MMAs retire
+            if (!(p.debug & 16)) umma_commit(emptyB + 8 * sb);     // weights slot free once these MMAs retire
           }
           __syncwarp();
           first = 1;
