@@ -41,7 +41,7 @@ struct Params {
   int NB;
   int a_bytes, b_bytes;
   int gn_groups;
-  int debug;   // development switches (env DPC_TC_DEBUG): 1 = no MMA issue, 2 = no TMA loads/waits, 4 = no epilogue stores
+  int AB, tmem_cols;
 };
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -50,24 +50,29 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   const long long t0 = clock64();
-  while (true) {
-    uint32_t done;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (done) return;
+  while (!mbar_try(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {
       printf("dpc conv3d_tcgen05: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
              threadIdx.x, bar, parity);
       __trap();
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try(bar, parity)) mbar_wait_slow(bar, parity);
 }
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3, int c4) {
@@ -120,9 +125,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr));
 }
 
-__device__ long long g_tc_ts[16];   // development timestamps of one CTA (debug & 8)
-#define TS(i) do { if ((p.debug & 8) && blockIdx.x == 1000) g_tc_ts[i] = clock64(); } while (0)
-
 template <int N>
 __global__ void __launch_bounds__(256, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
@@ -136,36 +138,27 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   const uint32_t bars = b_buf + p.NB * p.b_bytes;         // 8-byte mbarriers
   const uint32_t fullA = bars, emptyA = bars + 8 * NA;
   const uint32_t fullB = bars + 16 * NA, emptyB = fullB + 8 * p.NB;
-  const uint32_t accum_bar = emptyB + 8 * p.NB;
-  const uint32_t tmem_slot = accum_bar + 8;
-  __shared__ double s_stat[2][8];
+  const uint32_t acc_full = emptyB + 8 * p.NB, acc_empty = acc_full + 16;
+  const uint32_t tmem_slot = acc_empty + 16;
+  __shared__ double s_part[4][16];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) TS(0);
-  const int tile = blockIdx.x;
-  const int tf = tile % p.tiles_f;
-  const int f = (tile / p.tiles_f) % p.F;
-  const int b = tile / (p.tiles_f * p.F);
-  const int mu_tile = tf * p.S * 128;                 // first padded-flat output position of this tile
-  const int hq = mu_tile / p.pitch;                   // image row of that position
-  const int mu0 = mu_tile - hq * p.pitch;             // its offset inside the row
-  const int npos = p.H * p.pitch - mu_tile;           // positions left in the frame
-  const int nsub = (npos >= p.S * 128) ? p.S : (npos + 127) / 128;
   const int Cin = p.C1 + p.C2;
   const int nch = Cin / KCH, nch1 = p.C1 / KCH;
-  const int tmem_cols = (p.S * N <= 32) ? 32 : (p.S * N <= 64) ? 64 : (p.S * N <= 128) ? 128 : (p.S * N <= 256) ? 256 : 512;
+  const int nblk = 3 * nch;
+  const int AB = p.AB;                                   // TMEM accumulator sets (2 = epilogue overlaps the next tile)
+  const int ntiles = p.B * p.F * p.tiles_f;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, 1); }
     for (int i = 0; i < p.NB; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, 1); }
-    mbar_init(accum_bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
   }
-  if (threadIdx.x < 16) s_stat[threadIdx.x >> 3][threadIdx.x & 7] = 0.0;
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -174,173 +167,219 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
-  if (threadIdx.x == 0) TS(1);
 
-  if (warp == 0 && lane == 0 && !(p.debug & 2)) {
+  if (warp == 0 && lane == 0) {
     // ------------------------------------------- TMA producer -------------------------------------------
     // Issue order follows slot availability: the weight boxes of block j that fit the ring go first, then the A box of
-    // block j+1 (its buffer frees when block j-1 retires) cut into APARTS row slabs interleaved with the remaining
+    // the next block (its buffer frees when block j-1 retires) cut into APARTS row slabs interleaved with the remaining
     // weight boxes, so a 90 KB A transfer never sits in front of a weight box the tensor pipe is about to need.
-    const int nblk = 3 * nch;
     const int rows_part = (p.R + APARTS - 1) / APARTS;
-    auto issue_a_part = [&](int j, int part) {
-      const int dt = j / nch, ch = j - dt * nch;
-      const CUtensorMap* mp = (ch < nch1) ? &tmA1 : &tmA2;
-      const int c0 = (ch < nch1) ? ch * KCH : (ch - nch1) * KCH;
-      const int sa = j % NA;
-      const int r0 = part * rows_part;
-      if (r0 >= p.R) return;
-      if (part == 0) {
-        mbar_wait(emptyA + 8 * sa, ((j / NA) & 1) ^ 1);
+    int sa = 0, sb = 0;
+    uint32_t pha = 1, phb = 1;                            // producer parity: first pass over a fresh ring does not block
+    // state of the A box being fetched (one block ahead of the weight stream)
+    int a_tile = blockIdx.x, a_blk = 0, a_part = 0;
+    auto issue_a_part = [&]() {
+      if (a_tile >= ntiles) return;
+      const int tf = a_tile % p.tiles_f;
+      const int f = (a_tile / p.tiles_f) % p.F;
+      const int b = a_tile / (p.tiles_f * p.F);
+      const int hq = (tf * p.S * 128) / p.pitch;
+      const int dt = a_blk / nch, ch = a_blk - dt * nch;
+      const bool src1 = ch < nch1;
+      const int c0 = src1 ? ch * KCH : (ch - nch1) * KCH;
+      const int r0 = a_part * rows_part;
+      if (a_part == 0) {
+        mbar_wait(emptyA + 8 * sa, pha);
         mbar_expect_tx(fullA + 8 * sa, (uint32_t)(p.R * p.pitch * ROW_BYTES));
       }
-      const CUtensorMap* mpp = (r0 + rows_part <= p.R) ? mp : ((ch < nch1) ? &tmA1t : &tmA2t);
-      tma_load_5d(a_buf + sa * p.a_bytes + (uint32_t)(r0 * p.pitch * ROW_BYTES), mpp, fullA + 8 * sa, c0, -1,
-                  hq - 1 + r0, f + dt - 1, b);
-    };
-    int ib = 0;
-    for (int part = 0; part < APARTS; ++part) issue_a_part(0, part);
-    for (int j = 0; j < nblk; ++j) {
-      const int dt = j / nch, ch = j - dt * nch;
-      int next_part = 0;
-      for (int t9 = 0; t9 < 9; ++t9) {
-        const int sb = ib % p.NB;
-        mbar_wait(emptyB + 8 * sb, ((ib / p.NB) & 1) ^ 1);
-        mbar_expect_tx(fullB + 8 * sb, (uint32_t)p.b_bytes);
-        tma_load_2d(b_buf + sb * p.b_bytes, &tmW, fullB + 8 * sb, (dt * 9 + t9) * Cin + ch * KCH, 0);
-        ++ib;
-        if (j + 1 < nblk && t9 + 1 >= p.NB - 1 && next_part < APARTS) issue_a_part(j + 1, next_part++);
+      if (r0 < p.R) {
+        const CUtensorMap* mp = (r0 + rows_part <= p.R) ? (src1 ? &tmA1 : &tmA2) : (src1 ? &tmA1t : &tmA2t);
+        tma_load_5d(a_buf + sa * p.a_bytes + (uint32_t)(r0 * p.pitch * ROW_BYTES), mp, fullA + 8 * sa, c0, -1,
+                    hq - 1 + r0, f + dt - 1, b);
       }
-      while (j + 1 < nblk && next_part < APARTS) issue_a_part(j + 1, next_part++);
+      if (++a_part == APARTS) {
+        a_part = 0;
+        if (++sa == NA) { sa = 0; pha ^= 1; }
+        if (++a_blk == nblk) { a_blk = 0; a_tile += gridDim.x; }
+      }
+    };
+    for (int i = 0; i < APARTS; ++i) issue_a_part();      // A box of the very first block
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      for (int j = 0; j < nblk; ++j) {
+        const int dt = j / nch, ch = j - dt * nch;
+        const int k0 = dt * 9 * Cin + ch * KCH;
+        int parts_left = APARTS;
+        for (int t9 = 0; t9 < 9; ++t9) {
+          mbar_wait(emptyB + 8 * sb, phb);
+          mbar_expect_tx(fullB + 8 * sb, (uint32_t)p.b_bytes);
+          tma_load_2d(b_buf + sb * p.b_bytes, &tmW, fullB + 8 * sb, k0 + t9 * Cin, 0);
+          if (++sb == p.NB) { sb = 0; phb ^= 1; }
+          if (t9 + 2 >= p.NB && parts_left > 0) { issue_a_part(); --parts_left; }
+        }
+        while (parts_left > 0) { issue_a_part(); --parts_left; }
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------- MMA issuer ---------------------------------------------
-    // The whole warp walks the pipeline (warp-uniform control flow keeps descriptors in uniform registers); one
-    // elected lane issues.  Descriptors are advanced by integer adds on the 16-byte-unit start-address field:
-    // +2 per K=8 step (32 B), +1024 per 128-row sub-tile, +(dh*pitch+dw)*8 per tap.
+    // The whole warp walks the pipeline (warp-uniform control flow, no divisions in the loop); one elected lane
+    // issues.  Descriptors are advanced by integer adds on the 16-byte-unit start-address field: +2 per K=8 step
+    // (32 B), +1024 per 128-row sub-tile, +8 per dw, +8*pitch per dh.
     // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    int ia = 0, ib = 0;
-    uint32_t first = 0;                                                // becomes 1 after the first K block
-    for (int dt = 0; dt < 3; ++dt) {
-      for (int ch = 0; ch < nch; ++ch) {
-        const int sa = ia % NA;
-        if (!(p.debug & 2)) mbar_wait(fullA + 8 * sa, (ia / NA) & 1);
+    const uint64_t adesc_buf0 = umma_desc(a_buf);
+    const uint64_t bdesc_buf0 = umma_desc(b_buf);
+    const uint32_t a_step = (uint32_t)(p.a_bytes >> 4), b_step = (uint32_t)(p.b_bytes >> 4);
+    const uint32_t dh_step = (uint32_t)(p.pitch * (ROW_BYTES / 16));
+    int sa = 0, sb = 0, ab = 0;
+    uint32_t pha = 0, phb = 0, phacc = 1;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int tf = tile % p.tiles_f;
+      const int mu_tile = tf * p.S * 128;
+      const int mu0 = mu_tile - (mu_tile / p.pitch) * p.pitch;
+      const int npos = p.H * p.pitch - mu_tile;
+      const int nsub = (npos >= p.S * 128) ? p.S : (npos + 127) / 128;
+      mbar_wait(acc_empty + 8 * ab, phacc);               // epilogue has drained this accumulator set
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tacc = tmem_base + (uint32_t)(ab * p.S * N);
+      uint32_t first = 0;
+      for (int j = 0; j < nblk; ++j) {
+        mbar_wait(fullA + 8 * sa, pha);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (ia == 0 && lane == 0) TS(2);
-        const uint64_t adesc0 = umma_desc(a_buf + sa * p.a_bytes + (uint32_t)(mu0 * ROW_BYTES));
-        for (int t9 = 0; t9 < 9; ++t9) {
-          const int dh = t9 / 3, dw = t9 - dh * 3;
-          const int sb = ib % p.NB;
-          if (!(p.debug & 2)) mbar_wait(fullB + 8 * sb, (ib / p.NB) & 1);
-          if (!(p.debug & 32)) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint64_t bdesc = umma_desc(b_buf + sb * p.b_bytes);
-          const uint64_t adesc = adesc0 + (uint64_t)((dh * p.pitch + dw) * (ROW_BYTES / 16));
-          if ((p.debug & 64) ? (lane == 0) : elect_one()) {
+        uint64_t adesc_dh = adesc_buf0 + (uint64_t)(sa * a_step + mu0 * (ROW_BYTES / 16));
+#pragma unroll 1
+        for (int dh = 0; dh < 3; ++dh, adesc_dh += dh_step) {
+          uint64_t adesc = adesc_dh;
+#pragma unroll 1
+          for (int dw = 0; dw < 3; ++dw, adesc += ROW_BYTES / 16) {
+            mbar_wait(fullB + 8 * sb, phb);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint64_t bdesc = bdesc_buf0 + (uint64_t)(sb * b_step);
+            if (elect_one()) {
 #pragma unroll
-            for (int s = 0; s < MAXS; ++s) {
-              if (s < nsub && !(p.debug & 1)) {
+              for (int s = 0; s < MAXS; ++s) {
+                if (s < nsub) {
 #pragma unroll
-                for (int k = 0; k < KCH / 8; ++k)
-                  umma_tf32(tmem_base + (uint32_t)(s * N), adesc + (uint64_t)(s * (128 * ROW_BYTES / 16) + 2 * k),
-                            bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
+                  for (int k = 0; k < KCH / 8; ++k)
+                    umma_tf32(tacc + (uint32_t)(s * N), adesc + (uint64_t)(s * (128 * ROW_BYTES / 16) + 2 * k),
+                              bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
+                }
               }
+              umma_commit(emptyB + 8 * sb);               // weight slot is free once these MMAs retire
             }
-            if (!(p.debug & 16)) umma_commit(emptyB + 8 * sb);     // weights slot free once these MMAs retire
+            __syncwarp();
+            first = 1;
+            if (++sb == p.NB) { sb = 0; phb ^= 1; }
           }
-          __syncwarp();
-          first = 1;
-          ++ib;
         }
         if (elect_one()) umma_commit(emptyA + 8 * sa);
         __syncwarp();
-        ++ia;
+        if (++sa == NA) { sa = 0; pha ^= 1; }
       }
+      if (elect_one()) umma_commit(acc_full + 8 * ab);   // accumulators of this tile are complete
+      __syncwarp();
+      if (++ab == AB) { ab = 0; phacc ^= 1; }
     }
-    if (elect_one()) umma_commit(accum_bar);
-    __syncwarp();
-    if (lane == 0) TS(3);
   } else if (warp >= 4) {
     // ------------------------------------------- epilogue -----------------------------------------------
-    const int q = warp - 4;                       // TMEM lane quarter == warp_id % 4
-    mbar_wait(accum_bar, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (threadIdx.x == 128) TS(4);
+    const int q = warp - 4;                               // TMEM lane quarter == warp_id % 4
     const bool do_stats = p.gn_stats != nullptr;
     // GroupNorm(8): group width N/8 columns, GPC groups per 32-column chunk; one (sum, sumsq) pair per group
-    constexpr int GPC = 256 / N;        // 4, 2, 1 for N = 64, 128, 256
-    constexpr int GW = 32 / GPC;        // columns of one group inside a chunk
-    double gs[8], gq[8];
+    constexpr int GPC = 256 / N;                          // 4, 2, 1 for N = 64, 128, 256
+    constexpr int GW = 32 / GPC;                          // columns of one group inside a chunk
+    int ab = 0;
+    uint32_t phacc = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int tf = tile % p.tiles_f;
+      const int f = (tile / p.tiles_f) % p.F;
+      const int b = tile / (p.tiles_f * p.F);
+      const int mu_tile = tf * p.S * 128;
+      const int npos = p.H * p.pitch - mu_tile;
+      const int nsub = (npos >= p.S * 128) ? p.S : (npos + 127) / 128;
+      float fs[8], fq[8];                                 // per-thread partial sums (<= 64 values each) in fp32
 #pragma unroll
-    for (int g = 0; g < 8; ++g) gs[g] = gq[g] = 0.0;
-    for (int s = 0; s < nsub; ++s) {
-      const int mu = mu_tile + s * 128 + q * 32 + lane;   // padded-flat output position inside the frame
-      const int h = mu / p.pitch, w = mu - h * p.pitch;
-      const bool valid = (h < p.H) && (w < p.W);
-      const size_t m = (((size_t)b * p.F + f) * p.H + h) * p.W + w;
-      float* dst = p.y + m * N;
+      for (int g = 0; g < 8; ++g) fs[g] = fq[g] = 0.f;
+      mbar_wait(acc_full + 8 * ab, phacc);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.S * N);
+      for (int s = 0; s < nsub; ++s) {
+        const int mu = mu_tile + s * 128 + q * 32 + lane;   // padded-flat output position inside the frame
+        const int h = mu / p.pitch, w = mu - h * p.pitch;
+        const bool valid = (h < p.H) && (w < p.W);
+        const size_t m = (((size_t)b * p.F + f) * p.H + h) * p.W + w;
+        float* dst = p.y + m * N;
 #pragma unroll
-      for (int c = 0; c < N / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(s * N + c * 32), v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        float o[32];
+        for (int c = 0; c < N / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tacc + (uint32_t)(s * N + c * 32), v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float o[32];
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + c * 32 + j));
-          o[j] = __uint_as_float(v[j]) + bv.x;
-          o[j + 1] = __uint_as_float(v[j + 1]) + bv.y;
-          o[j + 2] = __uint_as_float(v[j + 2]) + bv.z;
-          o[j + 3] = __uint_as_float(v[j + 3]) + bv.w;
-        }
-        if (valid && !(p.debug & 4)) {
+          for (int j = 0; j < 32; j += 4) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + c * 32 + j));
+            o[j] = __uint_as_float(v[j]) + bv.x;
+            o[j + 1] = __uint_as_float(v[j + 1]) + bv.y;
+            o[j + 2] = __uint_as_float(v[j + 2]) + bv.z;
+            o[j + 3] = __uint_as_float(v[j + 3]) + bv.w;
+          }
+          if (valid) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(dst + c * 32 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-          if (do_stats) {
+            for (int j = 0; j < 32; j += 4)
+              __stcs(reinterpret_cast<float4*>(dst + c * 32 + j), make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]));
+            if (do_stats) {
 #pragma unroll
-            for (int g = 0; g < GPC; ++g) {
-              float ps = 0.f, pq = 0.f;
+              for (int g = 0; g < GPC; ++g) {
+                float ps = 0.f, pq = 0.f;
 #pragma unroll
-              for (int j = 0; j < GW; ++j) {
-                ps += o[g * GW + j];
-                pq += o[g * GW + j] * o[g * GW + j];
+                for (int j = 0; j < GW; ++j) {
+                  ps += o[g * GW + j];
+                  pq = fmaf(o[g * GW + j], o[g * GW + j], pq);
+                }
+                fs[(c * GPC + g) % 8] += ps;              // (c*GPC + g) < 8 by construction
+                fq[(c * GPC + g) % 8] += pq;
               }
-              gs[(c * GPC + g) % 8] += (double)ps;   // (c*GPC + g) < 8 by construction
-              gq[(c * GPC + g) % 8] += (double)pq;
             }
           }
         }
       }
-    }
-    if (threadIdx.x == 128) TS(5);
-    if (do_stats) {
+      // accumulator set drained: hand it back to the MMA warp before the (slower) statistics reduction
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty + 8 * ab) : "memory");
+      if (++ab == AB) { ab = 0; phacc ^= 1; }
+      if (do_stats) {
+        // recursive-halving warp reduction of 16 doubles (8 sums, 8 sums of squares): 16 exchanges instead of 80
+        double v[16];
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        double a = gs[g], bq = gq[g];
+        for (int g = 0; g < 8; ++g) { v[g] = (double)fs[g]; v[8 + g] = (double)fq[g]; }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { a += shfl_xor_double(a, o); bq += shfl_xor_double(bq, o); }
-        if (lane == 0) {
-          atomicAdd(&s_stat[0][g], a);
-          atomicAdd(&s_stat[1][g], bq);
+        for (int half = 8, mask = 16; half >= 1; half >>= 1, mask >>= 1) {
+          const bool up = (lane & mask) != 0;
+#pragma unroll
+          for (int i = 0; i < half; ++i) {
+            const double keep = up ? v[i + half] : v[i];
+            const double send = up ? v[i] : v[i + half];
+            v[i] = keep + shfl_xor_double(send, mask);
+          }
         }
-      }
-      // the four epilogue warps rendezvous on a named barrier, then publish one atomic per (group, statistic)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int et = threadIdx.x - 128;
-      if (et < 16) {
-        const int which = et >> 3, grp = et & 7;
-        atomicAdd(p.gn_stats + ((size_t)b * 8 + grp) * 2 + which, s_stat[which][grp]);
+        v[0] += shfl_xor_double(v[0], 1);                 // lane L now holds the warp total of value index L >> 1
+        asm volatile("bar.sync 1, 128;" ::: "memory");    // previous tile's s_part has been consumed
+        if ((lane & 1) == 0) s_part[q][lane >> 1] = v[0];
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int et = threadIdx.x - 128;
+        if (et < 16) {
+          const int slot = et;   // after the halving lane L holds value index L >> 1 (bit k of L selects bit k-1)
+          const double tot = s_part[0][et] + s_part[1][et] + s_part[2][et] + s_part[3][et];
+          const int which = slot >> 3, grp = slot & 7;
+          atomicAdd(p.gn_stats + ((size_t)b * 8 + grp) * 2 + which, tot);
+        }
       }
     }
   }
-  if (threadIdx.x == 128) TS(6);
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (threadIdx.x == 0) TS(7);
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
 }
 
@@ -395,7 +434,14 @@ static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMa
     DPC_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  const unsigned grid = (unsigned)((size_t)p.B * p.F * p.tiles_f);
+  const size_t ntiles = (size_t)p.B * p.F * p.tiles_f;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    DPC_CUDA(cudaGetDevice(&dev));
+    DPC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const unsigned grid = (unsigned)(ntiles < (size_t)num_sms ? ntiles : (size_t)num_sms);   // persistent: one CTA per SM
   conv3d_tc_kernel<N><<<grid, 256, smem, st>>>(a1, a2, a1t, a2t, wm, p);
   DPC_LAUNCH_CHECK();
   return 0;
@@ -422,7 +468,6 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   DPC_CHECK_ARG(c.x1 && c.w && c.y && (c.C2 == 0 || c.x2));
   Params p;
   p.bias = c.bias; p.y = c.y; p.gn_stats = c.gn_stats; p.gn_groups = c.gn_groups;
-  { const char* e = getenv("DPC_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
   p.B = c.B; p.F = F; p.H = H; p.W = W; p.C1 = c.C1; p.C2 = c.C2; p.Cout = c.Cout;
   p.pitch = W + 2;
   const int frame_pos = H * p.pitch;
@@ -438,6 +483,8 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   }
   if ((size_t)NA * p.a_bytes + 3 * (size_t)p.b_bytes + 1024 + 256 > budget || p.R > 256) return -2;
   p.S = S;
+  p.AB = (2 * S * c.Cout <= 512) ? 2 : 1;
+  { int need = p.AB * S * c.Cout; p.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512; }
   p.tiles_f = (frame_pos + S * 128 - 1) / (S * 128);
   int NB = (int)((budget - 1024 - 256 - (size_t)NA * p.a_bytes) / p.b_bytes);
   if (NB > 9) NB = 9;
@@ -469,9 +516,3 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   return launch<256>(a1, a2, a1t, a2t, wm, p, smem, st);
 }
 
-extern "C" int dpc_tc_debug_timestamps(long long* out16) {
-  using namespace dpc;
-  DPC_CUDA(cudaDeviceSynchronize());
-  DPC_CUDA(cudaMemcpyFromSymbol(out16, dpc::tc::g_tc_ts, sizeof(long long) * 16));
-  return 0;
-}

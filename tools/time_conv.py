@@ -22,13 +22,6 @@ def run(B, Fr, S, cin, cout, tc=True, reps=5):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     fl = 2.0 * B * Fr * S * S * cin * cout * 27
-    if int(os.environ.get('DPC_TC_DEBUG', '0')) & 8:
-        import ctypes
-        arr = (ctypes.c_longlong * 16)()
-        _lib.lib().dpc_tc_debug_timestamps(arr)
-        t = list(arr)
-        print("  ts deltas (cycles): prologue %d | to first A landed %d | mma loop %d | accum wait after mma-issue-end %d | epilogue loop %d | stats %d | teardown %d | total %d"
-              % (t[1]-t[0], t[2]-t[1], t[3]-t[2], t[4]-t[3], t[5]-t[4], t[6]-t[5], t[7]-t[6], t[7]-t[0]))
     print(f"DPC_TC_DEBUG={os.environ.get('DPC_TC_DEBUG','0')} B={B} S={S} {cin}->{cout}: {ms:.3f} ms {fl/ms/1e9:.0f} TFLOP/s", flush=True)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 run(B, 32, 64, 64, 64); run(B, 32, 32, 128, 128); run(B, 32, 16, 256, 256)
