@@ -37,7 +37,8 @@ struct Params {
   double* gn_stats;
   int B, F, H, W;
   int C1, C2, Cout;
-  int S, pitch, R, tiles_f;   // sub-tiles per CTA, smem row pitch (W+2), box rows, tiles per frame
+  int S, pitch, R, tiles_f;   // sub-tiles per CTA, smem row pitch, box rows, tiles per frame
+  int ndw;                    // 1: one halo box (pitch W+2) serves all nine in-plane taps; 3: one box per dw (pitch W)
   int NB;
   int a_bytes, b_bytes;
   int gn_groups;
@@ -145,7 +146,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Cin = p.C1 + p.C2;
   const int nch = Cin / KCH, nch1 = p.C1 / KCH;
-  const int nblk = 3 * nch;
+  const int nblk = 3 * nch * p.ndw;                     // A boxes per tile
+  const int ntap = 9 / p.ndw;                            // weight boxes per A box
   const int AB = p.AB;                                   // TMEM accumulator sets (2 = epilogue overlaps the next tile)
   const int ntiles = p.B * p.F * p.tiles_f;
 
@@ -184,7 +186,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       const int f = (a_tile / p.tiles_f) % p.F;
       const int b = a_tile / (p.tiles_f * p.F);
       const int hq = (tf * p.S * 128) / p.pitch;
-      const int dt = a_blk / nch, ch = a_blk - dt * nch;
+      const int dt = a_blk / (nch * p.ndw);
+      const int rem = a_blk - dt * nch * p.ndw;
+      const int ch = rem / p.ndw, dwb = rem - ch * p.ndw;
       const bool src1 = ch < nch1;
       const int c0 = src1 ? ch * KCH : (ch - nch1) * KCH;
       const int r0 = a_part * rows_part;
@@ -194,7 +198,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       }
       if (r0 < p.R) {
         const CUtensorMap* mp = (r0 + rows_part <= p.R) ? (src1 ? &tmA1 : &tmA2) : (src1 ? &tmA1t : &tmA2t);
-        tma_load_5d(a_buf + sa * p.a_bytes + (uint32_t)(r0 * p.pitch * ROW_BYTES), mp, fullA + 8 * sa, c0, -1,
+        tma_load_5d(a_buf + sa * p.a_bytes + (uint32_t)(r0 * p.pitch * ROW_BYTES), mp, fullA + 8 * sa, c0, dwb - 1,
                     hq - 1 + r0, f + dt - 1, b);
       }
       if (++a_part == APARTS) {
@@ -206,15 +210,19 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     for (int i = 0; i < APARTS; ++i) issue_a_part();      // A box of the very first block
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int j = 0; j < nblk; ++j) {
-        const int dt = j / nch, ch = j - dt * nch;
-        const int k0 = dt * 9 * Cin + ch * KCH;
+        const int dt = j / (nch * p.ndw);
+        const int rem = j - dt * nch * p.ndw;
+        const int ch = rem / p.ndw, dwb = rem - ch * p.ndw;
+        // weight column of tap (dt, dh, dw): ((dt*3 + dh)*3 + dw)*Cin + ch*32; per box either all nine (dh,dw) or the three dh
+        const int k0 = (dt * 9 + dwb) * Cin + ch * KCH;
+        const int kstep = (p.ndw == 1) ? Cin : 3 * Cin;
         int parts_left = APARTS;
-        for (int t9 = 0; t9 < 9; ++t9) {
+        for (int t = 0; t < ntap; ++t) {
           mbar_wait(emptyB + 8 * sb, phb);
           mbar_expect_tx(fullB + 8 * sb, (uint32_t)p.b_bytes);
-          tma_load_2d(b_buf + sb * p.b_bytes, &tmW, fullB + 8 * sb, k0 + t9 * Cin, 0);
+          tma_load_2d(b_buf + sb * p.b_bytes, &tmW, fullB + 8 * sb, k0 + t * kstep, 0);
           if (++sb == p.NB) { sb = 0; phb ^= 1; }
-          if (t9 + 2 >= p.NB && parts_left > 0) { issue_a_part(); --parts_left; }
+          if ((t + 2 >= p.NB || t + 1 >= ntap - 1) && parts_left > 0) { issue_a_part(); --parts_left; }
         }
         while (parts_left > 0) { issue_a_part(); --parts_left; }
       }
@@ -230,6 +238,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     const uint64_t bdesc_buf0 = umma_desc(b_buf);
     const uint32_t a_step = (uint32_t)(p.a_bytes >> 4), b_step = (uint32_t)(p.b_bytes >> 4);
     const uint32_t dh_step = (uint32_t)(p.pitch * (ROW_BYTES / 16));
+    const int ndw_in = (p.ndw == 1) ? 3 : 1;              // dw taps served from one A box
     int sa = 0, sb = 0, ab = 0;
     uint32_t pha = 0, phb = 0, phacc = 1;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -250,7 +259,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         for (int dh = 0; dh < 3; ++dh, adesc_dh += dh_step) {
           uint64_t adesc = adesc_dh;
 #pragma unroll 1
-          for (int dw = 0; dw < 3; ++dw, adesc += ROW_BYTES / 16) {
+          for (int dw = 0; dw < ndw_in; ++dw, adesc += ROW_BYTES / 16) {
             mbar_wait(fullB + 8 * sb, phb);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint64_t bdesc = bdesc_buf0 + (uint64_t)(sb * b_step);
@@ -461,7 +470,7 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
       c.ntaps == 27 && c.st == 1 && c.sh == 1 && c.sw == 1 && c.pt == 1 && c.ph == 1 && c.pw == 1 && c.Fo == F &&
       c.Ho == H && c.Wo == W && c.oh_mul == 1 && c.ow_mul == 1 && c.Hfull == H && c.Wfull == W && c.out_layout == 0 &&
       c.residual == nullptr && c.precise == 0 && c.C1 % KCH == 0 && c.C2 % KCH == 0 && c.C1 > 0 &&
-      (c.Cout == 64 || c.Cout == 128 || c.Cout == 256) && c.Npad == c.Cout && W >= 2 && W + 2 <= 256 && H >= 1 &&
+      (c.Cout == 64 || c.Cout == 128 || c.Cout == 256) && c.Npad == c.Cout && W >= 4 && W + 2 <= 256 && H >= 1 &&
       c.Kpad == 27 * (c.C1 + c.C2);
   if (!shape_ok) return -2;
   if (c.gn_stats && c.gn_groups != 8) return -2;   // the epilogue is specialised for GroupNorm(8), the reference default
@@ -469,7 +478,10 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   Params p;
   p.bias = c.bias; p.y = c.y; p.gn_stats = c.gn_stats; p.gn_groups = c.gn_groups;
   p.B = c.B; p.F = F; p.H = H; p.W = W; p.C1 = c.C1; p.C2 = c.C2; p.Cout = c.Cout;
-  p.pitch = W + 2;
+  // small frames: padding columns (W+2)/W and the 128-row quantisation of the padded-flat domain waste too much of
+  // the tensor pipe, so fall back to one box per dw (pitch W, three times the A traffic, zero wasted rows)
+  p.ndw = (W >= 32) ? 1 : 3;
+  p.pitch = (p.ndw == 1) ? W + 2 : W;
   const int frame_pos = H * p.pitch;
   int S = 512 / c.Cout;
   if (S > MAXS) S = MAXS;
@@ -477,6 +489,7 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   const size_t budget = 227 * 1024 - 2048;
   p.b_bytes = c.Cout * ROW_BYTES;
   for (;; --S) {
+    // rows needed: offset inside the first row (< pitch) + S*128 positions + two more image rows (+2 positions in halo mode)
     p.R = (p.pitch - 1 + S * 128 + 2 * p.pitch + 2 + p.pitch - 1) / p.pitch;
     p.a_bytes = ((p.R * p.pitch * ROW_BYTES + 1023) / 1024) * 1024;
     if ((size_t)NA * p.a_bytes + 3 * (size_t)p.b_bytes + 1024 + 256 <= budget || S == 1) break;
