@@ -60,7 +60,7 @@ _SIGNATURES = {
                             C.c_int32, C.c_int32, C.c_float, c_fp], C.c_int),
     "dpc_layernorm_channels": ([c_fp, c_fp, c_fp, C.c_int64, C.c_int32, C.c_float, c_fp], C.c_int),
     "dpc_pack_input": ([c_fp, c_fp] + [C.c_int32] * 8 + [c_fp], C.c_int),
-    "dpc_temporal_attention": ([c_fp] * 5 + [C.c_int32] * 5 + [c_fp], C.c_int),
+    "dpc_temporal_attention": ([c_fp] * 5 + [C.c_int32] * 6 + [c_fp], C.c_int),
     "dpc_spatial_attention": ([c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_spatial_linear_attention": ([c_fp, c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_time_embed": ([c_fp] * 8 + [C.c_int32, C.c_int32, c_fp], C.c_int),
@@ -202,9 +202,9 @@ def pack_input(x, out, B, F, Ctot, c0, Cin, H, W, Cpad):
 
 
 @_timed("temporal_attention")
-def temporal_attention(qkv, rope_cos, rope_sin, pos_bias, out, B, F, HW, heads, use_rope=True):
+def temporal_attention(qkv, rope_cos, rope_sin, pos_bias, out, B, F, HW, heads, use_rope=True, precise=False):
     check(lib().dpc_temporal_attention(ptr(qkv), ptr(rope_cos), ptr(rope_sin), ptr(pos_bias), ptr(out), B, F, HW, heads,
-                                       1 if use_rope else 0, stream_ptr()), "dpc_temporal_attention")
+                                       1 if use_rope else 0, 1 if precise else 0, stream_ptr()), "dpc_temporal_attention")
     LaunchCounter.count += 1
 
 

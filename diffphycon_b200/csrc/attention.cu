@@ -139,6 +139,210 @@ temporal_attention_kernel(const float* __restrict__ qkv, const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// temporal attention, F <= 32, tensor-core version: one warp per (sample, pixel, head).
+//   stage : coalesced 128-byte row segments of q|k|v -> scale, RoPE -> shared memory (row stride 36 floats)
+//   S     : Q K^T as 2x4 m16n8k8 TF32 MMAs per k-step (ldmatrix fragments), + relative bias, key mask, row softmax
+//           (row reductions stay inside a quad: 2 shuffles)
+//   O     : P V with the accumulator fragments of S reused directly as the A operand: lane (g,t) holds P[row][2t],
+//           P[row][2t+1] of every 8-key block, so the MMA's k index is mapped to keys (2t, 2t+1) and the V fragment is
+//           read with the same permutation — no shuffles, no round trip through shared memory
+//   store : O -> shared memory -> coalesced 128-byte row segments
+// PRECISE = 3xTF32 error-compensated products (fp32-class, the reference's einsum precision); otherwise operands are
+// rounded to TF32 with cvt.rna.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <bool PRECISE>
+__device__ __forceinline__ void mma_op(float (&d)[4], const float (&a)[4], float b0, float b1) {
+  if constexpr (!PRECISE) {
+    const uint32_t au[4] = {to_tf32(a[0]), to_tf32(a[1]), to_tf32(a[2]), to_tf32(a[3])};
+    mma_tf32_16x8x8(d, au, to_tf32(b0), to_tf32(b1));
+  } else {
+    uint32_t ab[4], as[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      ab[i] = __float_as_uint(a[i]) & 0xffffe000u;
+      as[i] = __float_as_uint(a[i] - __uint_as_float(ab[i]));
+    }
+    const uint32_t b0b = __float_as_uint(b0) & 0xffffe000u, b1b = __float_as_uint(b1) & 0xffffe000u;
+    const uint32_t b0s = __float_as_uint(b0 - __uint_as_float(b0b)), b1s = __float_as_uint(b1 - __uint_as_float(b1b));
+    mma_tf32_16x8x8(d, as, b0b, b1b);
+    mma_tf32_16x8x8(d, ab, b0s, b1s);
+    mma_tf32_16x8x8(d, ab, b0b, b1b);
+  }
+}
+
+template <bool PRECISE>
+__global__ void __launch_bounds__(128)
+temporal_attention_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ rope_cos,
+                              const float* __restrict__ rope_sin, const float* __restrict__ pos_bias,
+                              float* __restrict__ out, int64_t total_warps, int F, int HW, int heads, int use_rope) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int LD = DH + 4;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* Qs = sm + (size_t)warp * 3 * 32 * LD;
+  float* Ks = Qs + 32 * LD;
+  float* Vs = Ks + 32 * LD;
+  const int C3 = 3 * heads * DH, hid = heads * DH;
+  const int g = lane >> 2, t = lane & 3;
+  const int lf = lane >> 3, lc = (lane & 7) * 4;      // staging: frame-in-group, first channel of this lane's float4
+
+  for (int64_t wg = (int64_t)blockIdx.x * 4 + warp; wg < total_warps; wg += (int64_t)gridDim.x * 4) {
+    const int head = (int)(wg % heads);
+    const int64_t bp = wg / heads;
+    const int pix = (int)(bp % HW);
+    const int64_t b = bp / HW;
+    // ---- stage q, k, v ----
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int f = it * 4 + lf;
+      float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f), k4 = q4, v4 = q4;
+      if (f < F) {
+        const float* row = qkv + (((size_t)b * F + f) * HW + pix) * C3 + head * DH + lc;
+        q4 = __ldcs(reinterpret_cast<const float4*>(row));
+        k4 = __ldcs(reinterpret_cast<const float4*>(row + hid));
+        v4 = __ldcs(reinterpret_cast<const float4*>(row + 2 * hid));
+        q4.x = __fmul_rn(q4.x, ATT_SCALE); q4.y = __fmul_rn(q4.y, ATT_SCALE);
+        q4.z = __fmul_rn(q4.z, ATT_SCALE); q4.w = __fmul_rn(q4.w, ATT_SCALE);
+        if (use_rope) {
+          const float4 cs = __ldg(reinterpret_cast<const float4*>(rope_cos + (size_t)f * DH + lc));
+          const float4 sn = __ldg(reinterpret_cast<const float4*>(rope_sin + (size_t)f * DH + lc));
+          // t*cos + rotate_half(t)*sin with rotate_half: (x0, x1) -> (-x1, x0), separately rounded like the reference
+          float4 r;
+          r.x = __fadd_rn(__fmul_rn(q4.x, cs.x), __fmul_rn(-q4.y, sn.x));
+          r.y = __fadd_rn(__fmul_rn(q4.y, cs.y), __fmul_rn(q4.x, sn.y));
+          r.z = __fadd_rn(__fmul_rn(q4.z, cs.z), __fmul_rn(-q4.w, sn.z));
+          r.w = __fadd_rn(__fmul_rn(q4.w, cs.w), __fmul_rn(q4.z, sn.w));
+          q4 = r;
+          r.x = __fadd_rn(__fmul_rn(k4.x, cs.x), __fmul_rn(-k4.y, sn.x));
+          r.y = __fadd_rn(__fmul_rn(k4.y, cs.y), __fmul_rn(k4.x, sn.y));
+          r.z = __fadd_rn(__fmul_rn(k4.z, cs.z), __fmul_rn(-k4.w, sn.z));
+          r.w = __fadd_rn(__fmul_rn(k4.w, cs.w), __fmul_rn(k4.z, sn.w));
+          k4 = r;
+        }
+      }
+      *reinterpret_cast<float4*>(Qs + f * LD + lc) = q4;
+      *reinterpret_cast<float4*>(Ks + f * LD + lc) = k4;
+      *reinterpret_cast<float4*>(Vs + f * LD + lc) = v4;
+    }
+    __syncwarp();
+    // ---- S = Q K^T ----
+    float s[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s[mt][nt][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      float a[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        const float* qa = Qs + (mt * 16 + g) * LD + ks * 8 + t;
+        a[mt][0] = qa[0]; a[mt][1] = qa[8 * LD]; a[mt][2] = qa[4]; a[mt][3] = qa[8 * LD + 4];
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float* kb = Ks + (nt * 8 + g) * LD + ks * 8 + t;   // B[k = d][n = key] = K[key][d]
+        const float b0 = kb[0], b1 = kb[4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) mma_op<PRECISE>(s[mt][nt], a[mt], b0, b1);
+      }
+    }
+    // ---- bias, key mask, softmax over keys (row = mt*16 + g + 8*h, col = nt*8 + 2t + e) ----
+    float inv[2][2];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = mt * 16 + g + 8 * h;
+        const float* brow = (pos_bias && row < F) ? pos_bias + ((size_t)head * F + row) * F : nullptr;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = nt * 8 + 2 * t + e;
+            float v = s[mt][nt][2 * h + e];
+            if (brow && col < F) v += __ldg(brow + col);
+            if (col >= F) v = -INFINITY;
+            s[mt][nt][2 * h + e] = v;
+            mx = fmaxf(mx, v);
+          }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        float l = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const float pv = expf(s[mt][nt][2 * h + e] - mx);
+            s[mt][nt][2 * h + e] = pv;
+            l += pv;
+          }
+        l += __shfl_xor_sync(0xffffffffu, l, 1);
+        l += __shfl_xor_sync(0xffffffffu, l, 2);
+        inv[mt][h] = 1.0f / l;
+      }
+    // ---- O = P V (k index of the MMA mapped to keys 8*kb + 2t, 8*kb + 2t + 1) ----
+    float o[2][4][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int dn = 0; dn < 4; ++dn)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[mt][dn][e] = 0.f;
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {
+      float a[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        a[mt][0] = s[mt][kb][0] * inv[mt][0];   // (row g,   key 2t)
+        a[mt][1] = s[mt][kb][2] * inv[mt][1];   // (row g+8, key 2t)
+        a[mt][2] = s[mt][kb][1] * inv[mt][0];   // (row g,   key 2t+1)
+        a[mt][3] = s[mt][kb][3] * inv[mt][1];   // (row g+8, key 2t+1)
+      }
+#pragma unroll
+      for (int dn = 0; dn < 4; ++dn) {
+        const float* vb = Vs + (kb * 8 + 2 * t) * LD + dn * 8 + g;
+        const float b0 = vb[0], b1 = vb[LD];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) mma_op<PRECISE>(o[mt][dn], a[mt], b0, b1);
+      }
+    }
+    __syncwarp();   // every lane is done reading Qs: reuse it as the output staging tile
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int dn = 0; dn < 4; ++dn) {
+        float* od = Qs + (mt * 16 + g) * LD + dn * 8 + 2 * t;
+        *reinterpret_cast<float2*>(od) = make_float2(o[mt][dn][0], o[mt][dn][1]);
+        *reinterpret_cast<float2*>(od + 8 * LD) = make_float2(o[mt][dn][2], o[mt][dn][3]);
+      }
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int f = it * 4 + lf;
+      if (f < F) {
+        const float4 v = *reinterpret_cast<const float4*>(Qs + f * LD + lc);
+        __stcs(reinterpret_cast<float4*>(out + (((size_t)b * F + f) * HW + pix) * hid + head * DH + lc), v);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // mid-block spatial softmax attention: one thread per query token, K/V streamed through shared memory in tiles of 32
 // tokens with an online softmax.  grid = (ceil(HW/128), heads, B*F).
 // ------------------------------------------------------------------------------------------------------------
@@ -345,7 +549,7 @@ linattn_apply_kernel(const float* __restrict__ qkv, const float* __restrict__ ct
 
 extern "C" int dpc_temporal_attention(const float* qkv, const float* rope_cos, const float* rope_sin,
                                       const float* pos_bias, float* out, int32_t B, int32_t F, int32_t HW,
-                                      int32_t heads, int32_t use_rope, void* stream) {
+                                      int32_t heads, int32_t use_rope, int32_t precise, void* stream) {
   using namespace dpc;
   DPC_CHECK_ARG(qkv && out && B > 0 && F > 0 && F <= 64 && HW > 0 && heads > 0);
   DPC_CHECK_ARG(!use_rope || (rope_cos && rope_sin));
@@ -355,9 +559,19 @@ extern "C" int dpc_temporal_attention(const float* qkv, const float* rope_cos, c
   if (blocks > cap) blocks = cap;
   cudaStream_t st = (cudaStream_t)stream;
   if (F <= 32) {
-    const size_t smem = (size_t)4 * 2 * 32 * 36 * sizeof(float);
-    temporal_attention_kernel<1><<<(unsigned)blocks, 128, smem, st>>>(qkv, rope_cos, rope_sin, pos_bias, out, total, F, HW,
-                                                                      heads, use_rope);
+    const size_t smem = (size_t)4 * 3 * 32 * 36 * sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+      DPC_CUDA(cudaFuncSetAttribute(temporal_attention_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      DPC_CUDA(cudaFuncSetAttribute(temporal_attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = true;
+    }
+    if (precise)
+      temporal_attention_mma_kernel<true><<<(unsigned)blocks, 128, smem, st>>>(qkv, rope_cos, rope_sin, pos_bias, out, total, F,
+                                                                              HW, heads, use_rope);
+    else
+      temporal_attention_mma_kernel<false><<<(unsigned)blocks, 128, smem, st>>>(qkv, rope_cos, rope_sin, pos_bias, out, total, F,
+                                                                               HW, heads, use_rope);
   } else {
     const size_t smem = (size_t)4 * 2 * 64 * 36 * sizeof(float);
     static bool configured = false;

@@ -537,7 +537,7 @@ class Unet3D_with_Conv3D(nn.Module):
             pool.put(xn)
             att = pool.get(m * hid)
             if kind == "temporal":
-                _lib.temporal_attention(qkv, G["rope.cos"], G["rope.sin"], G["pos_bias"], att, B, F, h * w, heads, True)
+                _lib.temporal_attention(qkv, G["rope.cos"], G["rope.sin"], G["pos_bias"], att, B, F, h * w, heads, True, precise)
             elif kind == "spatial":
                 _lib.spatial_attention(qkv, att, B * F, h * w, heads)
             else:

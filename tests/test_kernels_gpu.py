@@ -214,24 +214,28 @@ def test_layernorm_channels(C):
     assert rel_err(out.reshape(-1), ref) <= TOL_F32
 
 
+@pytest.mark.parametrize("precise", [True, False])
 @pytest.mark.parametrize("Fr", [4, 20, 32, 40, 64])
-def test_temporal_attention(Fr):
+def test_temporal_attention(Fr, precise):
+    """F <= 32: tensor-core kernel (3xTF32 = fp32 class, or TF32 operands); F > 32: fp32 SIMT kernel."""
     gen = g(9)
     B, HW, heads = 2, 24, 4
     qkv = torch.randn(B, Fr, HW, 384, generator=gen)
     freqs = 1.0 / (10000 ** (torch.arange(0, 32, 2).float() / 32))
     ang = (torch.arange(Fr).float()[:, None] * freqs[None, :]).repeat_interleave(2, dim=-1)
     bias = torch.randn(heads, Fr, Fr, generator=gen)
+    tol = TOL_F32 if (precise or Fr > 32) else 2e-3
     out = torch.empty(B, Fr, HW, 128, device=DEV)
-    _lib.temporal_attention(qkv.to(DEV), ang.cos().to(DEV), ang.sin().to(DEV), bias.to(DEV), out, B, Fr, HW, heads, True)
+    _lib.temporal_attention(qkv.to(DEV), ang.cos().to(DEV), ang.sin().to(DEV), bias.to(DEV), out, B, Fr, HW, heads, True,
+                            precise)
     ref = torch.empty(out.numel(), dtype=torch.float64)
     emu.temporal_attention(qkv.reshape(-1).double(), ang.cos().double(), ang.sin().double(), bias.double(), ref, B, Fr, HW,
                            heads, True)
-    assert rel_err(out.reshape(-1), ref) <= TOL_F32
+    assert rel_err(out.reshape(-1), ref) <= tol
     out2 = torch.empty_like(out)
-    _lib.temporal_attention(qkv.to(DEV), None, None, None, out2, B, Fr, HW, heads, False)
+    _lib.temporal_attention(qkv.to(DEV), None, None, None, out2, B, Fr, HW, heads, False, precise)
     emu.temporal_attention(qkv.reshape(-1).double(), None, None, None, ref, B, Fr, HW, heads, False)
-    assert rel_err(out2.reshape(-1), ref) <= TOL_F32
+    assert rel_err(out2.reshape(-1), ref) <= tol
 
 
 @pytest.mark.parametrize("HW", [16, 100, 256])
@@ -371,6 +375,7 @@ def test_conv3d_tcgen05(case):
     assert rel_err(y, ref) <= TOL_TF32
     y2, stats2, _ = run_conv(x1.to(DEV), wp, 27, tcgen05=False, **kw)
     assert rel_err(y, y2) <= 2e-4        # both truncate the same TF32 operands; only the accumulation order differs
+    # per-thread partial sums are fp32 (<= 64 values), everything above is double: 2e-6 of the L1 mass
     v = y.double().reshape(B, -1, 8, Cout // 8)
-    assert torch.allclose(stats[:, :, 0], v.sum(dim=(1, 3)), rtol=1e-6, atol=1e-6)
-    assert torch.allclose(stats[:, :, 1], (v * v).sum(dim=(1, 3)), rtol=1e-6, atol=1e-6)
+    assert ((stats[:, :, 0] - v.sum(dim=(1, 3))).abs() <= 2e-6 * v.abs().sum(dim=(1, 3)) + 1e-9).all()
+    assert ((stats[:, :, 1] - (v * v).sum(dim=(1, 3))).abs() <= 2e-6 * (v * v).sum(dim=(1, 3)) + 1e-9).all()
