@@ -249,7 +249,7 @@ class GaussianDiffusion(nn.Module):
         times = torch.linspace(-1, total - 1, steps=steps_n + 1)
         times = list(reversed(times.int().tolist()))
         time_pairs = list(zip(times[:-1], times[1:]))
-        img = torch.randn(shape, device=device)
+        img = self.sample_noise(list(shape), device)
         init = init.to(device).float().contiguous()
         img[:, 0, 0] = init
         it = time_pairs
@@ -284,7 +284,7 @@ class GaussianDiffusion(nn.Module):
             cc = (1 - alpha_next - sigma ** 2).sqrt()
             c.sqrt_alpha_next, c.c, c.ddim_sigma, c.last = float(alpha_next.sqrt()), float(cc), float(sigma), 0
             if noise is None:
-                noise = torch.randn_like(img)
+                noise = self.sample_noise(list(img.shape), img.device)
         out = torch.empty_like(img)
         _lib.guided_step(True, img.contiguous(), eps_j, eps_w, noise, init, g, c, out, None, b, f, h, w)
         return out

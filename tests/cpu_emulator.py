@@ -203,6 +203,17 @@ def guided_step(ddim, x, eps_joint, eps_w, noise, init, g, c, x_out, x_start_out
         x_start_out.copy_(xs)
 
 
+def install_raw():
+    """Same as install() without pytest (used inside spawned worker processes)."""
+    from diffphycon_b200 import _lib, unet3d
+    for name in ("conv", "groupnorm_silu", "layernorm_channels", "pack_input", "temporal_attention",
+                 "spatial_attention", "spatial_linear_attention", "time_embed", "time_proj", "predict_x_start",
+                 "guided_step"):
+        setattr(_lib, name, globals()[name])
+    _lib.stream_ptr = lambda: None
+    unet3d._require_cuda = lambda x: None
+
+
 def install(monkeypatch):
     """Route diffphycon_b200._lib's launch wrappers to the emulators above (tests only)."""
     from diffphycon_b200 import _lib
