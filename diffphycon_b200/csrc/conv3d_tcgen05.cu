@@ -29,16 +29,20 @@ constexpr int KCH = 32;            // channels per K block: 32 fp32 = one 128-by
 constexpr int ROW_BYTES = 128;
 constexpr int NA = 2;              // A ring depth
 constexpr int MAXS = 4;
+constexpr int NTHREADS_TC = 384;    // warps 0-3: TMA / MMA / TMEM alloc / idle, warps 4-11: two epilogue groups
 constexpr int APARTS = 3;           // the A box of a block is fetched as APARTS row slabs
 
 struct Params {
   const float* bias;
+  const float* residual;      // optional, indexed like y
   float* y;
   double* gn_stats;
   int B, F, H, W;
   int C1, C2, Cout;
   int S, pitch, R, tiles_f;   // sub-tiles per CTA, smem row pitch, box rows, tiles per frame
   int ndw;                    // 1: one halo box (pitch W+2) serves all nine in-plane taps; 3: one box per dw (pitch W)
+  int gemm;                   // 1: 1x1x1 conv / Linear layer (single tap, no halo)
+  int ldy, wrow0;             // output row pitch (floats) and first weight row / output column of this launch
   int NB;
   int a_bytes, b_bytes;
   int gn_groups;
@@ -127,7 +131,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
 }
 
 template <int N>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(NTHREADS_TC, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmA1t, const __grid_constant__ CUtensorMap tmA2t,
                  const __grid_constant__ CUtensorMap tmW, const Params p) {
@@ -141,20 +145,20 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   const uint32_t fullB = bars + 16 * NA, emptyB = fullB + 8 * p.NB;
   const uint32_t acc_full = emptyB + 8 * p.NB, acc_empty = acc_full + 16;
   const uint32_t tmem_slot = acc_empty + 16;
-  __shared__ double s_part[4][16];
+  __shared__ double s_part[8][16];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Cin = p.C1 + p.C2;
   const int nch = Cin / KCH, nch1 = p.C1 / KCH;
-  const int nblk = 3 * nch * p.ndw;                     // A boxes per tile
-  const int ntap = 9 / p.ndw;                            // weight boxes per A box
+  const int nblk = p.gemm ? nch : 3 * nch * p.ndw;       // A boxes per tile
+  const int ntap = p.gemm ? 1 : 9 / p.ndw;               // weight boxes per A box
   const int AB = p.AB;                                   // TMEM accumulator sets (2 = epilogue overlaps the next tile)
   const int ntiles = p.B * p.F * p.tiles_f;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, 1); }
     for (int i = 0; i < p.NB; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
@@ -186,9 +190,14 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       const int f = (a_tile / p.tiles_f) % p.F;
       const int b = a_tile / (p.tiles_f * p.F);
       const int hq = (tf * p.S * 128) / p.pitch;
-      const int dt = a_blk / (nch * p.ndw);
-      const int rem = a_blk - dt * nch * p.ndw;
-      const int ch = rem / p.ndw, dwb = rem - ch * p.ndw;
+      int dt = 1, ch = a_blk, dwb = 1, halo = 0;             // gemm: centre tap only, no halo
+      if (!p.gemm) {
+        dt = a_blk / (nch * p.ndw);
+        const int rem = a_blk - dt * nch * p.ndw;
+        ch = rem / p.ndw;
+        dwb = rem - ch * p.ndw;
+        halo = 1;
+      }
       const bool src1 = ch < nch1;
       const int c0 = src1 ? ch * KCH : (ch - nch1) * KCH;
       const int r0 = a_part * rows_part;
@@ -199,7 +208,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       if (r0 < p.R) {
         const CUtensorMap* mp = (r0 + rows_part <= p.R) ? (src1 ? &tmA1 : &tmA2) : (src1 ? &tmA1t : &tmA2t);
         tma_load_5d(a_buf + sa * p.a_bytes + (uint32_t)(r0 * p.pitch * ROW_BYTES), mp, fullA + 8 * sa, c0, dwb - 1,
-                    hq - 1 + r0, f + dt - 1, b);
+                    hq - halo + r0, f + dt - 1, b);
       }
       if (++a_part == APARTS) {
         a_part = 0;
@@ -210,9 +219,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     for (int i = 0; i < APARTS; ++i) issue_a_part();      // A box of the very first block
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int j = 0; j < nblk; ++j) {
-        const int dt = j / (nch * p.ndw);
-        const int rem = j - dt * nch * p.ndw;
-        const int ch = rem / p.ndw, dwb = rem - ch * p.ndw;
+        int dt = 0, ch = j, dwb = 0;
+        if (!p.gemm) {
+          dt = j / (nch * p.ndw);
+          const int rem = j - dt * nch * p.ndw;
+          ch = rem / p.ndw;
+          dwb = rem - ch * p.ndw;
+        }
         // weight column of tap (dt, dh, dw): ((dt*3 + dh)*3 + dw)*Cin + ch*32; per box either all nine (dh,dw) or the three dh
         const int k0 = (dt * 9 + dwb) * Cin + ch * KCH;
         const int kstep = (p.ndw == 1) ? Cin : 3 * Cin;
@@ -220,7 +233,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         for (int t = 0; t < ntap; ++t) {
           mbar_wait(emptyB + 8 * sb, phb);
           mbar_expect_tx(fullB + 8 * sb, (uint32_t)p.b_bytes);
-          tma_load_2d(b_buf + sb * p.b_bytes, &tmW, fullB + 8 * sb, k0 + t * kstep, 0);
+          tma_load_2d(b_buf + sb * p.b_bytes, &tmW, fullB + 8 * sb, k0 + t * kstep, p.wrow0);
           if (++sb == p.NB) { sb = 0; phb ^= 1; }
           if ((t + 2 >= p.NB || t + 1 >= ntap - 1) && parts_left > 0) { issue_a_part(); --parts_left; }
         }
@@ -238,7 +251,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     const uint64_t bdesc_buf0 = umma_desc(b_buf);
     const uint32_t a_step = (uint32_t)(p.a_bytes >> 4), b_step = (uint32_t)(p.b_bytes >> 4);
     const uint32_t dh_step = (uint32_t)(p.pitch * (ROW_BYTES / 16));
-    const int ndw_in = (p.ndw == 1) ? 3 : 1;              // dw taps served from one A box
+    const int ndw_in = p.gemm ? 1 : ((p.ndw == 1) ? 3 : 1);   // dw taps served from one A box
+    const int ndh_in = p.gemm ? 1 : 3;
     int sa = 0, sb = 0, ab = 0;
     uint32_t pha = 0, phb = 0, phacc = 1;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -256,7 +270,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint64_t adesc_dh = adesc_buf0 + (uint64_t)(sa * a_step + mu0 * (ROW_BYTES / 16));
 #pragma unroll 1
-        for (int dh = 0; dh < 3; ++dh, adesc_dh += dh_step) {
+        for (int dh = 0; dh < ndh_in; ++dh, adesc_dh += dh_step) {
           uint64_t adesc = adesc_dh;
 #pragma unroll 1
           for (int dw = 0; dw < ndw_in; ++dw, adesc += ROW_BYTES / 16) {
@@ -290,7 +304,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     }
   } else if (warp >= 4) {
     // ------------------------------------------- epilogue -----------------------------------------------
-    const int q = warp - 4;                               // TMEM lane quarter == warp_id % 4
+    const int q = warp & 3;                               // TMEM lane quarter == warp_id % 4
+    const int eg = (warp - 4) >> 2;                       // epilogue group 0/1: sub-tiles s = eg, eg+2
     const bool do_stats = p.gn_stats != nullptr;
     // GroupNorm(8): group width N/8 columns, GPC groups per 32-column chunk; one (sum, sumsq) pair per group
     constexpr int GPC = 256 / N;                          // 4, 2, 1 for N = 64, 128, 256
@@ -310,12 +325,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       mbar_wait(acc_full + 8 * ab, phacc);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.S * N);
-      for (int s = 0; s < nsub; ++s) {
+      for (int s = eg; s < nsub; s += 2) {
         const int mu = mu_tile + s * 128 + q * 32 + lane;   // padded-flat output position inside the frame
         const int h = mu / p.pitch, w = mu - h * p.pitch;
         const bool valid = (h < p.H) && (w < p.W);
         const size_t m = (((size_t)b * p.F + f) * p.H + h) * p.W + w;
-        float* dst = p.y + m * N;
+        float* dst = p.y + m * p.ldy + p.wrow0;
+        const float* res = p.residual ? p.residual + m * p.ldy + p.wrow0 : nullptr;
 #pragma unroll
         for (int c = 0; c < N / 32; ++c) {
           uint32_t v[32];
@@ -332,6 +348,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             o[j + 3] = __uint_as_float(v[j + 3]) + bv.w;
           }
           if (valid) {
+            if (res) {
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                const float4 rv = __ldcs(reinterpret_cast<const float4*>(res + c * 32 + j));
+                o[j] += rv.x; o[j + 1] += rv.y; o[j + 2] += rv.z; o[j + 3] += rv.w;
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               __stcs(reinterpret_cast<float4*>(dst + c * 32 + j), make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]));
@@ -372,13 +395,14 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           }
         }
         v[0] += shfl_xor_double(v[0], 1);                 // lane L now holds the warp total of value index L >> 1
-        asm volatile("bar.sync 1, 128;" ::: "memory");    // previous tile's s_part has been consumed
-        if ((lane & 1) == 0) s_part[q][lane >> 1] = v[0];
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");    // previous tile's s_part has been consumed
+        if ((lane & 1) == 0) s_part[warp - 4][lane >> 1] = v[0];
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         const int et = threadIdx.x - 128;
         if (et < 16) {
           const int slot = et;   // after the halving lane L holds value index L >> 1 (bit k of L selects bit k-1)
-          const double tot = s_part[0][et] + s_part[1][et] + s_part[2][et] + s_part[3][et];
+          const double tot = ((s_part[0][et] + s_part[1][et]) + (s_part[2][et] + s_part[3][et])) +
+                             ((s_part[4][et] + s_part[5][et]) + (s_part[6][et] + s_part[7][et]));
           const int which = slot >> 3, grp = slot & 7;
           atomicAdd(p.gn_stats + ((size_t)b * 8 + grp) * 2 + which, tot);
         }
@@ -451,7 +475,7 @@ static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMa
     DPC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
   const unsigned grid = (unsigned)(ntiles < (size_t)num_sms ? ntiles : (size_t)num_sms);   // persistent: one CTA per SM
-  conv3d_tc_kernel<N><<<grid, 256, smem, st>>>(a1, a2, a1t, a2t, wm, p);
+  conv3d_tc_kernel<N><<<grid, NTHREADS_TC, smem, st>>>(a1, a2, a1t, a2t, wm, p);
   DPC_LAUNCH_CHECK();
   return 0;
 }
@@ -466,38 +490,47 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   const dpc_conv_params& c = *pp;
   // ---- shape gate: anything else is served by dpc_conv_igemm (same numerics class) ----
   const int W = c.Wi, H = c.Hi, F = c.Fi;
-  const bool shape_ok =
-      c.ntaps == 27 && c.st == 1 && c.sh == 1 && c.sw == 1 && c.pt == 1 && c.ph == 1 && c.pw == 1 && c.Fo == F &&
-      c.Ho == H && c.Wo == W && c.oh_mul == 1 && c.ow_mul == 1 && c.Hfull == H && c.Wfull == W && c.out_layout == 0 &&
-      c.residual == nullptr && c.precise == 0 && c.C1 % KCH == 0 && c.C2 % KCH == 0 && c.C1 > 0 &&
-      (c.Cout == 64 || c.Cout == 128 || c.Cout == 256) && c.Npad == c.Cout && W >= 4 && W + 2 <= 256 && H >= 1 &&
-      c.Kpad == 27 * (c.C1 + c.C2);
-  if (!shape_ok) return -2;
+  const bool common_ok = c.st == 1 && c.sh == 1 && c.sw == 1 && c.Fo == F && c.Ho == H && c.Wo == W && c.oh_mul == 1 &&
+                         c.ow_mul == 1 && c.Hfull == H && c.Wfull == W && c.out_layout == 0 && c.precise == 0 &&
+                         c.C1 % KCH == 0 && c.C2 % KCH == 0 && c.C1 > 0 && W >= 4 && W + 2 <= 256 && H >= 1 &&
+                         c.Kpad == c.ntaps * (c.C1 + c.C2);
+  const bool conv_ok = common_ok && c.ntaps == 27 && c.pt == 1 && c.ph == 1 && c.pw == 1 && c.residual == nullptr &&
+                       (c.Cout == 64 || c.Cout == 128 || c.Cout == 256) && c.Npad == c.Cout;
+  // 1x1x1 conv / Linear: N tiles of 64 / 128 / 256 columns (e.g. the 384-wide qkv projection = 3 x 128)
+  const bool gemm_ok = common_ok && c.ntaps == 1 && c.pt == 0 && c.ph == 0 && c.pw == 0 && c.gn_stats == nullptr &&
+                       (c.Cout == 64 || c.Cout % 128 == 0) && c.Npad >= c.Cout;
+  if (!conv_ok && !gemm_ok) return -2;
   if (c.gn_stats && c.gn_groups != 8) return -2;   // the epilogue is specialised for GroupNorm(8), the reference default
   DPC_CHECK_ARG(c.x1 && c.w && c.y && (c.C2 == 0 || c.x2));
+  const bool gemm = !conv_ok;
+  const int Ntile = gemm ? (c.Cout == 64 ? 64 : (c.Cout == 256 ? 256 : 128)) : c.Cout;
   Params p;
-  p.bias = c.bias; p.y = c.y; p.gn_stats = c.gn_stats; p.gn_groups = c.gn_groups;
+  p.bias = c.bias; p.residual = c.residual; p.y = c.y; p.gn_stats = c.gn_stats; p.gn_groups = c.gn_groups;
   p.B = c.B; p.F = F; p.H = H; p.W = W; p.C1 = c.C1; p.C2 = c.C2; p.Cout = c.Cout;
+  p.gemm = gemm ? 1 : 0;
+  p.ldy = c.Cout;
+  p.wrow0 = 0;
   // small frames: padding columns (W+2)/W and the 128-row quantisation of the padded-flat domain waste too much of
   // the tensor pipe, so fall back to one box per dw (pitch W, three times the A traffic, zero wasted rows)
-  p.ndw = (W >= 32) ? 1 : 3;
+  p.ndw = (!gemm && W >= 32) ? 1 : 3;
   p.pitch = (p.ndw == 1) ? W + 2 : W;
   const int frame_pos = H * p.pitch;
-  int S = 512 / c.Cout;
+  int S = gemm ? 256 / Ntile : 512 / Ntile;            // gemm tiles are store-bound: keep two accumulator sets
   if (S > MAXS) S = MAXS;
   if (S > (frame_pos + 127) / 128) S = (frame_pos + 127) / 128;
   const size_t budget = 227 * 1024 - 2048;
-  p.b_bytes = c.Cout * ROW_BYTES;
+  p.b_bytes = Ntile * ROW_BYTES;
   for (;; --S) {
-    // rows needed: offset inside the first row (< pitch) + S*128 positions + two more image rows (+2 positions in halo mode)
-    p.R = (p.pitch - 1 + S * 128 + 2 * p.pitch + 2 + p.pitch - 1) / p.pitch;
+    // rows needed: offset inside the first row (< pitch) + S*128 positions (+ two more image rows + 2 positions of halo)
+    const int span = p.pitch - 1 + S * 128 + (gemm ? 0 : 2 * p.pitch + 2);
+    p.R = (span + p.pitch - 1) / p.pitch;
     p.a_bytes = ((p.R * p.pitch * ROW_BYTES + 1023) / 1024) * 1024;
     if ((size_t)NA * p.a_bytes + 3 * (size_t)p.b_bytes + 1024 + 256 <= budget || S == 1) break;
   }
   if ((size_t)NA * p.a_bytes + 3 * (size_t)p.b_bytes + 1024 + 256 > budget || p.R > 256) return -2;
   p.S = S;
-  p.AB = (2 * S * c.Cout <= 512) ? 2 : 1;
-  { int need = p.AB * S * c.Cout; p.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512; }
+  p.AB = (2 * S * Ntile <= 512) ? 2 : 1;
+  { int need = p.AB * S * Ntile; p.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512; }
   p.tiles_f = (frame_pos + S * 128 - 1) / (S * 128);
   int NB = (int)((budget - 1024 - 256 - (size_t)NA * p.a_bytes) / p.b_bytes);
   if (NB > 9) NB = 9;
@@ -521,11 +554,16 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
     a2 = a1;
     a2t = a1t;
   }
-  rc = make_w_map(&wm, c.w, c.Kpad, c.Npad, c.Cout);
+  rc = make_w_map(&wm, c.w, c.Kpad, c.Npad, Ntile);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  if (c.Cout == 64) return launch<64>(a1, a2, a1t, a2t, wm, p, smem, st);
-  if (c.Cout == 128) return launch<128>(a1, a2, a1t, a2t, wm, p, smem, st);
-  return launch<256>(a1, a2, a1t, a2t, wm, p, smem, st);
+  for (int n0 = 0; n0 < c.Cout; n0 += Ntile) {
+    p.wrow0 = n0;
+    p.bias = c.bias ? c.bias + n0 : nullptr;
+    if (Ntile == 64) rc = launch<64>(a1, a2, a1t, a2t, wm, p, smem, st);
+    else if (Ntile == 128) rc = launch<128>(a1, a2, a1t, a2t, wm, p, smem, st);
+    else rc = launch<256>(a1, a2, a1t, a2t, wm, p, smem, st);
+    if (rc) return rc;
+  }
+  return 0;
 }
-

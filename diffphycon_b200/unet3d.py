@@ -517,7 +517,7 @@ class Unet3D_with_Conv3D(nn.Module):
             pool.put(y1)
             if f"{name}.res.w" in P:
                 res = pool.get(m * cout)
-                conv(xa, ca, P[f"{name}.res.w"], P[f"{name}.res.b"], res, cout, lvl, "111", xb=xb, cb=cb)
+                conv(xa, ca, P[f"{name}.res.w"], P[f"{name}.res.b"], res, cout, lvl, "111", xb=xb, cb=cb, tc=self.use_tcgen05)
                 _lib.groupnorm_silu(y2, s2, P[f"{name}.block2.gamma"], P[f"{name}.block2.beta"], None, 0, 0, res, y2,
                                     B, rps, cout, groups)
                 pool.put(res)
@@ -533,7 +533,7 @@ class Unet3D_with_Conv3D(nn.Module):
             xn = pool.get(m * c)
             _lib.layernorm_channels(xa, P[f"{name}.gamma"], xn, m, c)
             qkv = pool.get(m * 3 * hid)
-            conv(xn, c, P[f"{name}.qkv.w"], None, qkv, 3 * hid, lvl, "111")
+            conv(xn, c, P[f"{name}.qkv.w"], None, qkv, 3 * hid, lvl, "111", tc=self.use_tcgen05)
             pool.put(xn)
             att = pool.get(m * hid)
             if kind == "temporal":
@@ -546,7 +546,7 @@ class Unet3D_with_Conv3D(nn.Module):
                 pool.put(ctx)
             pool.put(qkv)
             y = pool.get(m * c)
-            conv(att, hid, P[f"{name}.out.w"], P.get(f"{name}.out.b"), y, c, lvl, "111", residual=xa)
+            conv(att, hid, P[f"{name}.out.w"], P.get(f"{name}.out.b"), y, c, lvl, "111", residual=xa, tc=self.use_tcgen05)
             pool.put(att)
             return y
 

@@ -71,12 +71,14 @@ typedef struct dpc_conv_params {
 
 int dpc_conv_igemm(const dpc_conv_params* p, void* stream);
 
-/* 3x3x3 / pad 1 Conv3d on the 5th-generation tensor cores: TMA-tiled operand staging (one halo box per
- * (dt, 32-channel chunk, dw) shared by the three dh taps), tcgen05.mma kind::tf32, accumulators in TMEM.
- * Same arguments, weight packing and epilogue as dpc_conv_igemm.  Supported: ntaps == 27, unit stride, pad 1,
- * channels-last output, no residual, C1 % 32 == 0, C2 % 32 == 0, Cout in {64,128,256} == Npad, W % 8 == 0, 128 % W == 0,
- * 128/W <= H <= 256, gn_groups in {0, 8}.  Returns -2 (nothing launched) for any other shape so the host mirror can
- * use dpc_conv_igemm (same numerics class). */
+/* Conv3d 3x3x3 / pad 1 and 1x1x1 (= Linear over channels-last rows) on the 5th-generation tensor cores: persistent CTAs,
+ * TMA-tiled operand staging (3x3x3: one halo box per (dt, 32-channel chunk) shared by all nine in-plane taps),
+ * tcgen05.mma kind::tf32, accumulators double-buffered in TMEM.  Same arguments, weight packing and epilogue as
+ * dpc_conv_igemm (bias, residual for 1x1x1, GroupNorm(8) partial statistics for 3x3x3).
+ * Supported: unit stride, channels-last output, C1 % 32 == 0, C2 % 32 == 0, 4 <= W <= 254, precise == 0, and
+ *   ntaps == 27: pad 1, no residual, Cout in {64,128,256} == Npad, gn_groups in {0, 8};
+ *   ntaps == 1 : pad 0, no gn_stats, Cout == 64 or Cout % 128 == 0 (run as column tiles of 64/128/256).
+ * Returns -2 (nothing launched) for any other shape so the host mirror can use dpc_conv_igemm (same numerics class). */
 int dpc_conv3d_tcgen05(const dpc_conv_params* p, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------

@@ -379,3 +379,38 @@ def test_conv3d_tcgen05(case):
     v = y.double().reshape(B, -1, 8, Cout // 8)
     assert ((stats[:, :, 0] - v.sum(dim=(1, 3))).abs() <= 2e-6 * v.abs().sum(dim=(1, 3)) + 1e-9).all()
     assert ((stats[:, :, 1] - (v * v).sum(dim=(1, 3))).abs() <= 2e-6 * (v * v).sum(dim=(1, 3)) + 1e-9).all()
+
+
+TC_GEMM_CASES = [
+    # name, B, F, H, W, C1, C2, Cout, bias, residual
+    ("qkv_64_to_384", 2, 4, 16, 16, 64, 0, 384, False, False),
+    ("qkv_256_to_384_w8", 1, 6, 8, 8, 256, 0, 384, False, False),
+    ("out_128_to_64_res", 2, 3, 32, 32, 128, 0, 64, True, True),
+    ("out_128_to_256_res", 1, 4, 16, 16, 128, 0, 256, False, True),
+    ("res_concat_512_to_128", 1, 2, 16, 16, 256, 256, 128, True, False),
+    ("w64_64_to_384", 1, 2, 64, 64, 64, 0, 384, False, False),
+    ("w4_128_to_128", 1, 5, 4, 4, 128, 0, 128, True, True),
+]
+
+
+@pytest.mark.parametrize("case", TC_GEMM_CASES, ids=[c[0] for c in TC_GEMM_CASES])
+def test_linear_tcgen05(case):
+    """1x1x1 conv / Linear layers through the persistent TMA/tcgen05 kernel (column tiles of 64/128/256)."""
+    _, B, Fr, H, W, C1, C2, Cout, with_bias, with_res = case
+    gen = g(31)
+    x1 = torch.randn(B, Fr, H, W, C1, generator=gen)
+    x2 = torch.randn(B, Fr, H, W, C2, generator=gen) if C2 else None
+    w = torch.randn(Cout, C1 + C2, generator=gen) / (C1 + C2) ** 0.5
+    bias = torch.randn(Cout, generator=gen) if with_bias else None
+    res = torch.randn(B, Fr, H, W, Cout, generator=gen) if with_res else None
+    xin = torch.cat([x1, x2], -1) if C2 else x1
+    ref = xin.double() @ w.double().t()
+    if with_bias:
+        ref = ref + bias.double()
+    if with_res:
+        ref = ref + res.double()
+    y, _, ran_tc = run_conv(x1.to(DEV), packing.pack_linear(w.to(DEV)), 1, x2=x2.to(DEV) if C2 else None,
+                            bias=bias.to(DEV) if with_bias else None, residual=res.to(DEV) if with_res else None,
+                            cout=Cout, tcgen05=True)
+    assert ran_tc, "shape should be served by the tcgen05 kernel"
+    assert rel_err(y, ref) <= TOL_TF32
