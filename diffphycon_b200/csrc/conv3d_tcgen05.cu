@@ -145,6 +145,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   const uint32_t fullB = bars + 16 * NA, emptyB = fullB + 8 * p.NB;
   const uint32_t acc_full = emptyB + 8 * p.NB, acc_empty = acc_full + 16;
   const uint32_t tmem_slot = acc_empty + 16;
+  float* stage_all = reinterpret_cast<float*>(smem_raw + (base - raw) + NA * p.a_bytes + p.NB * p.b_bytes + 256);  // gemm mode only
   __shared__ double s_part[8][16];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -325,6 +326,47 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       mbar_wait(acc_full + 8 * ab, phacc);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.S * N);
+      if (p.gemm) {
+        // Linear / 1x1x1 epilogue: the tile is store-bound, so rows are staged through a per-warp shared-memory tile
+        // (32 rows x 36 floats, conflict-free float4 both ways) and written as 128-byte row segments: a warp store
+        // covers 4 rows x 128 B instead of 32 rows x 16 B.
+        float* stage = stage_all + (warp - 4) * (32 * 36);
+        const size_t frame_base = ((size_t)b * p.F + f) * (size_t)(p.H * p.W);
+        const int rsub = lane >> 3, cq = (lane & 7) * 4;
+        for (int s = eg; s < nsub; s += 2) {
+          const int mu_w = mu_tile + s * 128 + q * 32;        // first position of this warp's 32 rows
+#pragma unroll 1
+          for (int c = 0; c < N / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tacc + (uint32_t)(s * N + c * 32), v);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + c * 32 + j));
+              *reinterpret_cast<float4*>(stage + lane * 36 + j) =
+                  make_float4(__uint_as_float(v[j]) + bv.x, __uint_as_float(v[j + 1]) + bv.y,
+                              __uint_as_float(v[j + 2]) + bv.z, __uint_as_float(v[j + 3]) + bv.w);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + rsub;
+              const int mu = mu_w + r;
+              if (mu < p.H * p.W) {
+                float4 ov = *reinterpret_cast<const float4*>(stage + r * 36 + cq);
+                const size_t off = (frame_base + mu) * (size_t)p.ldy + p.wrow0 + c * 32 + cq;
+                if (p.residual) {
+                  const float4 rv = __ldcs(reinterpret_cast<const float4*>(p.residual + off));
+                  ov.x += rv.x; ov.y += rv.y; ov.z += rv.z; ov.w += rv.w;
+                }
+                __stcs(reinterpret_cast<float4*>(p.y + off), ov);
+              }
+            }
+            __syncwarp();
+          }
+        }
+      } else
       for (int s = eg; s < nsub; s += 2) {
         const int mu = mu_tile + s * 128 + q * 32 + lane;   // padded-flat output position inside the frame
         const int h = mu / p.pitch, w = mu - h * p.pitch;
@@ -525,17 +567,19 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
     const int span = p.pitch - 1 + S * 128 + (gemm ? 0 : 2 * p.pitch + 2);
     p.R = (span + p.pitch - 1) / p.pitch;
     p.a_bytes = ((p.R * p.pitch * ROW_BYTES + 1023) / 1024) * 1024;
-    if ((size_t)NA * p.a_bytes + 3 * (size_t)p.b_bytes + 1024 + 256 <= budget || S == 1) break;
+    if ((size_t)NA * p.a_bytes + 3 * (size_t)p.b_bytes + 1024 + 256 + 36864 <= budget || S == 1) break;
   }
-  if ((size_t)NA * p.a_bytes + 3 * (size_t)p.b_bytes + 1024 + 256 > budget || p.R > 256) return -2;
+  if ((size_t)NA * p.a_bytes + 3 * (size_t)p.b_bytes + 1024 + 256 + 36864 > budget || p.R > 256) return -2;
   p.S = S;
   p.AB = (2 * S * Ntile <= 512) ? 2 : 1;
   { int need = p.AB * S * Ntile; p.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512; }
   p.tiles_f = (frame_pos + S * 128 - 1) / (S * 128);
-  int NB = (int)((budget - 1024 - 256 - (size_t)NA * p.a_bytes) / p.b_bytes);
+  const size_t stage_bytes = gemm ? (size_t)8 * 32 * 36 * sizeof(float) : 0;
+  int NB = (int)((budget - 1024 - 256 - stage_bytes - (size_t)NA * p.a_bytes) / p.b_bytes);
   if (NB > 9) NB = 9;
+  if (NB < 2) return -2;
   p.NB = NB;
-  const size_t smem = (size_t)NA * p.a_bytes + (size_t)NB * p.b_bytes + 1024 + 256;
+  const size_t smem = (size_t)NA * p.a_bytes + (size_t)NB * p.b_bytes + 1024 + 256 + stage_bytes;
   // the A box is fetched as APARTS slabs of rows_part rows; the last slab may be shorter -> its own tensor map
   const int rows_part = (p.R + APARTS - 1) / APARTS;
   const int nfull = p.R / rows_part;
