@@ -430,91 +430,131 @@ spatial_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out,
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// spatial linear attention, pass A: context[d][e] = sum_n softmax_n(k)[d][n] * v[e][n] per (frame, head).
-// One CTA per (frame, head); lane = d, warps stride over pixels; v is read as broadcast float4.
+// spatial linear attention (conv3d.py:243-257), two kernels.
+// pass A: context[d][e] = sum_n softmax_n(k)[n][d] * v[n][e] per (frame, head).  One CTA (128 threads) per (frame, head).
+//   1) column max of k over the pixels: float4 loads, 8 lanes cover the 128-byte head slice of one pixel (coalesced)
+//   2) tiles of 64 pixels of k and v are staged in shared memory with coalesced float4 loads, k is exponentiated in
+//      place, then thread (d = lane, e-block = warp) owns 8 context entries: per pixel one conflict-free LDS of
+//      exp(k), two broadcast LDS.128 of v and 8 FMAs.  No cross-warp reduction, 8 accumulators per thread.
 // ------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 linattn_context_kernel(const float* __restrict__ qkv, float* __restrict__ ctx, int HW, int heads) {
-  __shared__ float s_red[8][DH];
+  constexpr int TP = 64;                       // pixels per tile
+  __shared__ __align__(16) float s_k[2][TP][DH];
+  __shared__ __align__(16) float s_v[2][TP][DH];
+  __shared__ float s_red[16][DH];
   __shared__ float s_max[DH];
-  __shared__ float s_ctx[DH][DH + 1];
+  __shared__ float s_sum[DH];
   const int head = blockIdx.x % heads;
   const int64_t bf = blockIdx.x / heads;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int C3 = 3 * heads * DH, hid = heads * DH;
   const float* kbase = qkv + (size_t)bf * HW * C3 + hid + head * DH;
   const float* vbase = kbase + hid;
+  const int prow = tid >> 3, pc = (tid & 7) * 4;   // 16 pixel rows x 8 float4 per pass
 
-  float mx = -INFINITY;
-  for (int n = warp; n < HW; n += 8) mx = fmaxf(mx, __ldg(kbase + (size_t)n * C3 + lane));
-  s_red[warp][lane] = mx;
-  for (int i = threadIdx.x; i < DH * (DH + 1); i += 256) (&s_ctx[0][0])[i] = 0.f;
+  // ---- 1) max over pixels ----
+  float4 mx4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+  for (int n = prow; n < HW; n += 16) {
+    const float4 k4 = __ldg(reinterpret_cast<const float4*>(kbase + (size_t)n * C3 + pc));
+    mx4.x = fmaxf(mx4.x, k4.x); mx4.y = fmaxf(mx4.y, k4.y); mx4.z = fmaxf(mx4.z, k4.z); mx4.w = fmaxf(mx4.w, k4.w);
+  }
+  s_red[prow][pc] = mx4.x; s_red[prow][pc + 1] = mx4.y; s_red[prow][pc + 2] = mx4.z; s_red[prow][pc + 3] = mx4.w;
   __syncthreads();
-  if (warp == 0) {
-    float m = s_red[0][lane];
+  if (tid < DH) {
+    float m = s_red[0][tid];
 #pragma unroll
-    for (int w = 1; w < 8; ++w) m = fmaxf(m, s_red[w][lane]);
-    s_max[lane] = m;
+    for (int r = 1; r < 16; ++r) m = fmaxf(m, s_red[r][tid]);
+    s_max[tid] = m;
   }
   __syncthreads();
-  mx = s_max[lane];
+  const float4 cmax = *reinterpret_cast<const float4*>(&s_max[pc]);
 
-  float c[DH];
+  // ---- 2) context accumulation over tiles ----
+  float acc[8];
 #pragma unroll
-  for (int e = 0; e < DH; ++e) c[e] = 0.f;
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
   float ksum = 0.f;
-  for (int n = warp; n < HW; n += 8) {
-    const float ek = expf(__ldg(kbase + (size_t)n * C3 + lane) - mx);
-    ksum += ek;
-    const float4* v4p = reinterpret_cast<const float4*>(vbase + (size_t)n * C3);
+  const int ntiles = (HW + TP - 1) / TP;
+  float4 kreg[4], vreg[4];
+  auto load_tile = [&](int tile) {
 #pragma unroll
-    for (int e = 0; e < DH; e += 4) {
-      const float4 v = __ldg(v4p + (e >> 2));
-      c[e] = fmaf(ek, v.x, c[e]);
-      c[e + 1] = fmaf(ek, v.y, c[e + 1]);
-      c[e + 2] = fmaf(ek, v.z, c[e + 2]);
-      c[e + 3] = fmaf(ek, v.w, c[e + 3]);
+    for (int i = 0; i < 4; ++i) {
+      const int n = tile * TP + prow + 16 * i;
+      if (n < HW) {
+        kreg[i] = __ldg(reinterpret_cast<const float4*>(kbase + (size_t)n * C3 + pc));
+        vreg[i] = __ldg(reinterpret_cast<const float4*>(vbase + (size_t)n * C3 + pc));
+      } else {
+        kreg[i] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);   // exp -> 0
+        vreg[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
-  }
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = prow + 16 * i;
+      *reinterpret_cast<float4*>(&s_k[buf][r][pc]) = make_float4(expf(kreg[i].x - cmax.x), expf(kreg[i].y - cmax.y),
+                                                                  expf(kreg[i].z - cmax.z), expf(kreg[i].w - cmax.w));
+      *reinterpret_cast<float4*>(&s_v[buf][r][pc]) = vreg[i];
+    }
+  };
+  load_tile(0);
+  store_tile(0);
   __syncthreads();
-  s_red[warp][lane] = ksum;
-  for (int w = 0; w < 8; ++w) {
-    if (warp == w) {
-#pragma unroll
-      for (int e = 0; e < DH; ++e) s_ctx[lane][e] += c[e];
+  for (int tile = 0; tile < ntiles; ++tile) {
+    const int buf = tile & 1;
+    if (tile + 1 < ntiles) load_tile(tile + 1);        // global loads of the next tile overlap the FMAs below
+#pragma unroll 8
+    for (int n = 0; n < TP; ++n) {
+      const float ek = s_k[buf][n][lane];
+      const float4 v0 = *reinterpret_cast<const float4*>(&s_v[buf][n][warp * 8]);
+      const float4 v1 = *reinterpret_cast<const float4*>(&s_v[buf][n][warp * 8 + 4]);
+      if (warp == 0) ksum += ek;
+      acc[0] = fmaf(ek, v0.x, acc[0]); acc[1] = fmaf(ek, v0.y, acc[1]);
+      acc[2] = fmaf(ek, v0.z, acc[2]); acc[3] = fmaf(ek, v0.w, acc[3]);
+      acc[4] = fmaf(ek, v1.x, acc[4]); acc[5] = fmaf(ek, v1.y, acc[5]);
+      acc[6] = fmaf(ek, v1.z, acc[6]); acc[7] = fmaf(ek, v1.w, acc[7]);
     }
+    if (tile + 1 < ntiles) store_tile(buf ^ 1);
     __syncthreads();
   }
-  // normalise by sum_n exp(k) and emit
-  float* dst = ctx + (size_t)blockIdx.x * DH * DH;
-  for (int i = threadIdx.x; i < DH * DH; i += 256) {
-    const int d = i >> 5, e = i & 31;
-    float tot = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) tot += s_red[w][d];
-    dst[i] = s_ctx[d][e] / tot;
-  }
+  if (warp == 0) s_sum[lane] = ksum;
+  __syncthreads();
+  const float inv = 1.0f / s_sum[lane];
+  float* dst = ctx + (size_t)blockIdx.x * DH * DH + lane * DH + warp * 8;   // [d][e]
+  *reinterpret_cast<float4*>(dst) = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+  *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
 }
 
-// pass B: out[n][e] = sum_d context[d][e] * (softmax_d(q[n])[d] * scale); one thread per (pixel, head).
+// pass B: out[n][e] = sum_d context[d][e] * (softmax_d(q[n])[d] * scale).  One CTA = 128 pixels of one (frame, head):
+// q rows are staged through shared memory with coalesced loads, thread-per-pixel math, coalesced stores.
 __global__ void __launch_bounds__(128)
 linattn_apply_kernel(const float* __restrict__ qkv, const float* __restrict__ ctx, float* __restrict__ out, int HW,
                      int heads) {
   __shared__ __align__(16) float s_ctx[DH][DH];
+  __shared__ __align__(16) float s_q[128][DH + 4];
   const int head = blockIdx.y;
   const int64_t bf = blockIdx.z;
+  const int tid = threadIdx.x;
   const float* cp = ctx + ((size_t)bf * heads + head) * DH * DH;
-  for (int i = threadIdx.x; i < DH * DH; i += 128) (&s_ctx[0][0])[i] = __ldg(cp + i);
-  __syncthreads();
-  const int tok = blockIdx.x * 128 + threadIdx.x;
-  if (tok >= HW) return;
+  for (int i = tid; i < DH * DH; i += 128) (&s_ctx[0][0])[i] = __ldg(cp + i);
   const int C3 = 3 * heads * DH, hid = heads * DH;
-  const float* row = qkv + ((size_t)bf * HW + tok) * C3 + head * DH;
+  const int tok0 = blockIdx.x * 128;
+  const int prow = tid >> 3, pc = (tid & 7) * 4;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = prow + 16 * i;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tok0 + r < HW) v = __ldcs(reinterpret_cast<const float4*>(qkv + ((size_t)bf * HW + tok0 + r) * C3 + head * DH + pc));
+    *reinterpret_cast<float4*>(&s_q[r][pc]) = v;
+  }
+  __syncthreads();
   float q[DH];
   float mx = -INFINITY;
 #pragma unroll
   for (int c = 0; c < DH; c += 4) {
-    float4 a = __ldcs(reinterpret_cast<const float4*>(row + c));
+    const float4 a = *reinterpret_cast<const float4*>(&s_q[tid][c]);
     q[c] = a.x; q[c + 1] = a.y; q[c + 2] = a.z; q[c + 3] = a.w;
     mx = fmaxf(mx, fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
   }
@@ -540,9 +580,16 @@ linattn_apply_kernel(const float* __restrict__ qkv, const float* __restrict__ ct
       o[e + 3] = fmaf(qs, c4.w, o[e + 3]);
     }
   }
-  float* orow = out + ((size_t)bf * HW + tok) * hid + head * DH;
 #pragma unroll
-  for (int e = 0; e < DH; e += 4) *reinterpret_cast<float4*>(orow + e) = make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]);
+  for (int e = 0; e < DH; e += 4) *reinterpret_cast<float4*>(&s_q[tid][e]) = make_float4(o[e], o[e + 1], o[e + 2], o[e + 3]);
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = prow + 16 * i;
+    if (tok0 + r < HW)
+      __stcs(reinterpret_cast<float4*>(out + ((size_t)bf * HW + tok0 + r) * hid + head * DH + pc),
+             *reinterpret_cast<const float4*>(&s_q[r][pc]));
+  }
 }
 
 }  // namespace dpc
@@ -600,7 +647,7 @@ extern "C" int dpc_spatial_linear_attention(const float* qkv, float* ctx_ws, flo
   using namespace dpc;
   DPC_CHECK_ARG(qkv && ctx_ws && out && BF > 0 && BF <= 65535 && HW > 0 && heads > 0);
   cudaStream_t st = (cudaStream_t)stream;
-  linattn_context_kernel<<<(unsigned)((int64_t)BF * heads), 256, 0, st>>>(qkv, ctx_ws, HW, heads);
+  linattn_context_kernel<<<(unsigned)((int64_t)BF * heads), 128, 0, st>>>(qkv, ctx_ws, HW, heads);
   DPC_LAUNCH_CHECK();
   dim3 grid((unsigned)((HW + 127) / 128), (unsigned)heads, (unsigned)BF);
   linattn_apply_kernel<<<grid, 128, 0, st>>>(qkv, ctx_ws, out, HW, heads);
