@@ -43,3 +43,63 @@ def burgers_unet_module():
 def burgers_diffusion_module():
     _prepare()
     return importlib.import_module("diffusion.diffusion_1d_burgers")
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# phi / evaluate_solver: the vendored PhiFlow 1.0.x predates NumPy 1.23 (indexing with a *list* of slices) and
+# Python 3.10 (collections.Iterable).  Instead of copying and patching its sources, the UNMODIFIED files are compiled
+# through an AST hook at import time: every `x[expr]` whose index is a general expression becomes `x[__phi_idx__(expr)]`
+# and __phi_idx__ turns a list that contains slices / None / Ellipsis into the tuple old NumPy treated it as.
+# ----------------------------------------------------------------------------------------------------------------
+import ast  # noqa: E402
+import builtins  # noqa: E402
+import collections  # noqa: E402
+import collections.abc  # noqa: E402
+from importlib.abc import MetaPathFinder  # noqa: E402
+from importlib.machinery import PathFinder, SourceFileLoader  # noqa: E402
+from unittest import mock  # noqa: E402
+
+
+def _phi_idx(i):
+    if isinstance(i, list) and any(isinstance(e, slice) or e is None or e is Ellipsis for e in i):
+        return tuple(i)
+    return i
+
+
+class _IndexFix(ast.NodeTransformer):
+    def visit_Subscript(self, node):
+        self.generic_visit(node)
+        if isinstance(node.slice, (ast.Name, ast.BinOp, ast.List, ast.ListComp, ast.Attribute, ast.Call)):
+            node.slice = ast.Call(func=ast.Name(id="__phi_idx__", ctx=ast.Load()), args=[node.slice], keywords=[])
+        return node
+
+
+class _FixLoader(SourceFileLoader):
+    def source_to_code(self, data, path, *, _optimize=-1):
+        tree = _IndexFix().visit(ast.parse(data, path))
+        ast.fix_missing_locations(tree)
+        return compile(tree, path, "exec", dont_inherit=True, optimize=_optimize)
+
+
+class _FixFinder(MetaPathFinder):
+    def find_spec(self, fullname, path, target=None):
+        if not (fullname == "phi" or fullname.startswith("phi.") or fullname == "dataset" or fullname.startswith("dataset.")):
+            return None
+        spec = PathFinder.find_spec(fullname, list(path) if path else [REFERENCE_ROOT])
+        if spec is not None and spec.origin and spec.origin.endswith(".py"):
+            spec.loader = _FixLoader(fullname, spec.origin)
+        return spec
+
+
+def evaluate_solver_module():
+    """reference dataset/apps/evaluate_solver.py (+ phi/) compiled through the index-fix hook; plotting stubbed."""
+    _prepare()
+    builtins.__phi_idx__ = _phi_idx
+    if not hasattr(collections, "Iterable"):
+        collections.Iterable = collections.abc.Iterable
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.pylab", "matplotlib.animation", "matplotlib.backends",
+                 "matplotlib.backends.backend_pdf", "imageio", "IPython", "IPython.display"):
+        sys.modules.setdefault(name, mock.MagicMock())
+    if not any(isinstance(f, _FixFinder) for f in sys.meta_path):
+        sys.meta_path.insert(0, _FixFinder())
+    return importlib.import_module("dataset.apps.evaluate_solver")
