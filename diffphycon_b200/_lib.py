@@ -70,6 +70,7 @@ _SIGNATURES = {
     "dpc_ddim_guided_step": ([c_fp] * 6 + [C.c_int32, C.POINTER(StepCoefs), c_fp, c_fp] + [C.c_int32] * 4 + [c_fp],
                              C.c_int),
     "dpc_predict_x_start": ([c_fp, c_fp, C.c_float, C.c_float, C.c_int32, c_fp, C.c_int64, c_fp], C.c_int),
+    "dpc_smoke_rollout": ([c_fp] * 14 + [C.c_int32] * 4 + [C.c_double, C.c_double, C.c_int32, c_fp], C.c_int),
 }
 
 EXPORTS = tuple(_SIGNATURES)
@@ -246,4 +247,14 @@ def guided_step(ddim, x, eps_joint, eps_w, noise, init, g, coefs: StepCoefs, x_o
 def predict_x_start(x, eps, sr, srm1, clip, out):
     check(lib().dpc_predict_x_start(ptr(x), ptr(eps), sr, srm1, 1 if clip else 0, ptr(out), x.numel(), stream_ptr()),
           "dpc_predict_x_start")
+    LaunchCounter.count += 1
+
+
+@_timed("smoke_rollout")
+def smoke_rollout(fluid_mask, velocity_mask, init_velocity, init_density, c1, c2, vel_ws, x_ws, dens_ws, densitys,
+                  zero_densitys, velocitys, smoke_out, iterations, B, nt, nx, T, dt, accuracy, max_iterations):
+    check(lib().dpc_smoke_rollout(ptr(fluid_mask), ptr(velocity_mask), ptr(init_velocity), ptr(init_density), ptr(c1), ptr(c2),
+                                  ptr(vel_ws), ptr(x_ws), ptr(dens_ws), ptr(densitys), ptr(zero_densitys), ptr(velocitys),
+                                  ptr(smoke_out), ptr(iterations), B, nt, nx, T, float(dt), float(accuracy),
+                                  int(max_iterations), stream_ptr()), "dpc_smoke_rollout")
     LaunchCounter.count += 1

@@ -170,6 +170,23 @@ int dpc_ddim_guided_step(const float* x, const float* eps_joint, const float* ep
 int dpc_predict_x_start(const float* x, const float* eps, float sqrt_recip, float sqrt_recipm1, int32_t clip,
                         float* x_start, int64_t n, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Post-sampling smoke rollout — dataset/apps/evaluate_solver.py:205-310 (solver), :118-147 (get_envolve) with
+ * phi/flow.py:294-327, phi/math/nd.py:332-427, :602-614, phi/math/scipy_backend.py:58-77, :181-185,
+ * phi/solver/sparse.py:27-119 and phi/solver/base.py:56-103 (plain CG, max|r| >= accuracy, <= max_iterations).
+ * One persistent CTA per trajectory runs all T-1 simulation steps in fp64 (the reference's NumPy precision).
+ * fluid_mask [127][127] int8 (1 fluid / 0 obstacle), velocity_mask [128][128][2] fp32 (component 0 = x faces),
+ * init_velocity [B][128][128][2], init_density [B][nx][nx], c1/c2 [B][nt][nx][nx] (tiled in space and time on the fly,
+ * es.py:223-227).  Workspaces: vel_ws B*2*128*128*2 doubles, x_ws B*127*127 doubles, dens_ws B*4*127*127 floats.
+ * Outputs: densitys / zero_densitys [B][T][128][128] fp32, velocitys [B][T][128][128][2] fp64, smoke_out [B][T] fp64
+ * (es.py:305), iterations [B][T] int32 (CG iterations of the step that produced frame t).
+ * ------------------------------------------------------------------------------------------------------- */
+int dpc_smoke_rollout(const int8_t* fluid_mask, const float* velocity_mask, const float* init_velocity,
+                      const float* init_density, const float* c1, const float* c2, double* vel_ws, double* x_ws,
+                      float* dens_ws, float* densitys, float* zero_densitys, double* velocitys, double* smoke_out,
+                      int32_t* iterations, int32_t B, int32_t nt, int32_t nx, int32_t T, double dt, double accuracy,
+                      int32_t max_iterations, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -196,4 +196,15 @@ def test_t5_buckets_match_oracle():
         assert torch.equal(unet3d._t5_buckets(n, 32, 32), uo.relative_position_bucket(rel, 32, 32))
 
 
+
+
+def test_rollout_masks_match_reference(golden_dir):
+    from diffphycon_b200 import smoke_rollout as sr
+    z = np.load(os.path.join(golden_dir, "smoke_rollout.npz"))
+    sim = sr.init_sim_128()
+    assert np.array_equal(sim.fluid_mask, z["fluid_mask"])
+    assert np.array_equal(sim.velocity_mask, z["velocity_mask"])
+    assert np.array_equal(sr.init_velocity_()[0], z["init_velocity"])
+
+
 _ = so
