@@ -133,6 +133,7 @@ def main():
     ap.add_argument("--no-tcgen05", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-rollout", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -285,6 +286,26 @@ def main():
                 "step_hbm_algorithmic_gbs": ALGO_BYTES_PER_SAMPLE_STEP * B / (ms_per_step / 1e3) / 1e9,
                 "step_hbm_frac": ALGO_BYTES_PER_SAMPLE_STEP * B / (ms_per_step / 1e3) / 1e9 / pk["hbm"]}
 
+    # ---- post-sampling rollout of the sampled controls, informational ----
+    rollout = None
+    if rank == 0 and not args.no_rollout:
+        from diffphycon_b200 import smoke_rollout as sr
+        sim = sr.init_sim_128()
+        ctrl = (x[:, :, 3:5] * torch.tensor([16.0, 20.0], device=dev).view(1, 1, 2, 1, 1)).contiguous()
+        c1, c2 = ctrl[:, :, 0].contiguous(), ctrl[:, :, 1].contiguous()
+        dens = (x[:, 0, 0] * 2.0).clamp(min=0).contiguous()
+        sr.solver_batch(sim, sr.init_velocity_(), dens[:1], c1[:1, :4].contiguous(), c2[:1, :4].contiguous(), 8)
+        torch.cuda.synchronize()
+        e0.record()
+        ro = sr.solver_batch(sim, sr.init_velocity_(), dens, c1, c2, 256)
+        e1.record()
+        torch.cuda.synchronize()
+        rms = e0.elapsed_time(e1)
+        rollout = {"trajectories": B, "frames": 256, "ms_total": rms, "trajectories_per_s": B / (rms / 1e3),
+                   "mean_cg_iterations": float(ro["iterations"][:, 1:].float().mean()),
+                   "note": "one persistent CTA per trajectory, fp64 CG with the reference's 500-iteration cap; the "
+                           "reference needs ~48 s per trajectory on one CPU core (SURVEY.md section 6)"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, sec, cores = cpu_reference_steps_per_s(2, 1)
@@ -300,7 +321,7 @@ def main():
                        "per_gpu_batch": B, "global_batch": B * world, "sharding": "independent trajectories per rank, no per-step collective",
                        "l2": "inputs larger than L2 (activations are GBs per layer)", "precision": args.precision,
                        "tcgen05": not args.no_tcgen05, "micro_batch": args.micro_batch or None},
-            "clocks": sampler.summary(), "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+            "clocks": sampler.summary(), "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "rollout": rollout,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
