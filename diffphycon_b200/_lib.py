@@ -70,6 +70,7 @@ _SIGNATURES = {
     "dpc_ddim_guided_step": ([c_fp] * 6 + [C.c_int32, C.POINTER(StepCoefs), c_fp, c_fp] + [C.c_int32] * 4 + [c_fp],
                              C.c_int),
     "dpc_predict_x_start": ([c_fp, c_fp, C.c_float, C.c_float, C.c_int32, c_fp, C.c_int64, c_fp], C.c_int),
+    "dpc_burgers_rollout": ([c_fp] * 3 + [C.c_int32] * 4 + [C.c_float] * 6 + [c_fp], C.c_int),
     "dpc_smoke_rollout": ([c_fp] * 14 + [C.c_int32] * 4 + [C.c_double, C.c_double, C.c_int32, c_fp], C.c_int),
 }
 
@@ -257,4 +258,11 @@ def smoke_rollout(fluid_mask, velocity_mask, init_velocity, init_density, c1, c2
                                   ptr(vel_ws), ptr(x_ws), ptr(dens_ws), ptr(densitys), ptr(zero_densitys), ptr(velocitys),
                                   ptr(smoke_out), ptr(iterations), B, nt, nx, T, float(dt), float(accuracy),
                                   int(max_iterations), stream_ptr()), "dpc_smoke_rollout")
+    LaunchCounter.count += 1
+
+
+@_timed("burgers_rollout")
+def burgers_rollout(u0, f, traj, N, s, Nt, steps, t0, t1, d0, d1, d2, dt):
+    check(lib().dpc_burgers_rollout(ptr(u0), ptr(f), ptr(traj), N, s, Nt, steps, t0, t1, d0, d1, d2, dt, stream_ptr()),
+          "dpc_burgers_rollout")
     LaunchCounter.count += 1

@@ -187,6 +187,12 @@ int dpc_smoke_rollout(const int8_t* fluid_mask, const float* velocity_mask, cons
                       int32_t* iterations, int32_t B, int32_t nt, int32_t nx, int32_t T, double dt, double accuracy,
                       int32_t max_iterations, void* stream);
 
+/* Burgers finite-difference rollout — dataset/apps/generate_burgers.py:207-299 (burgers_numeric_solve_free), stencils
+ * of Diff_mat_1D (:95-110).  u0 [N][s], f [N][Nt][s] -> traj [N][Nt+1][s] (u0 followed by one record per force window).
+ * t0,t1 = -/+ 1/(2dx), d0,d1,d2 = visc*(1,-2,1)/dx^2 as fp32 (host: generate_burgers.py:255-258), steps = ceil(T/dt). */
+int dpc_burgers_rollout(const float* u0, const float* f, float* traj, int32_t N, int32_t s, int32_t Nt, int32_t steps,
+                        float t0, float t1, float d0, float d1, float d2, float dt, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -103,3 +103,12 @@ def evaluate_solver_module():
     if not any(isinstance(f, _FixFinder) for f in sys.meta_path):
         sys.meta_path.insert(0, _FixFinder())
     return importlib.import_module("dataset.apps.evaluate_solver")
+
+
+def generate_burgers_module():
+    """reference dataset/apps/generate_burgers.py (imports h5py / IPython / matplotlib at module level: stubbed)."""
+    _prepare()
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.pylab", "matplotlib.animation", "IPython", "IPython.display",
+                 "h5py"):
+        sys.modules.setdefault(name, mock.MagicMock())
+    return importlib.import_module("dataset.apps.generate_burgers")
