@@ -286,6 +286,22 @@ def main():
                 "step_hbm_algorithmic_gbs": ALGO_BYTES_PER_SAMPLE_STEP * B / (ms_per_step / 1e3) / 1e9,
                 "step_hbm_frac": ALGO_BYTES_PER_SAMPLE_STEP * B / (ms_per_step / 1e3) / 1e9 / pk["hbm"]}
 
+    # ---- the single collective of the path: all-gather of the sampled controls [B,32,2,64,64] per rank (untimed step) ----
+    gather = None
+    if world > 1:
+        ctrl_local = x[:, :, 3:5].contiguous()
+        bucket = torch.empty(world * ctrl_local.shape[0], *ctrl_local.shape[1:], dtype=ctrl_local.dtype, device=dev)
+        dist.all_gather_into_tensor(bucket, ctrl_local)       # warm-up (NCCL communicator setup)
+        barrier()
+        e0.record()
+        dist.all_gather_into_tensor(bucket, ctrl_local)
+        e1.record()
+        torch.cuda.synchronize()
+        g_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(g_ms, op=dist.ReduceOp.MAX)
+        gather = {"collective": "all_gather(sampled controls)", "bytes_per_rank": ctrl_local.numel() * 4,
+                  "ms": float(g_ms.item()), "once_per_sampling_run": True}
+
     # ---- post-sampling rollout of the sampled controls, informational ----
     rollout = None
     if rank == 0 and not args.no_rollout:
@@ -321,7 +337,7 @@ def main():
                        "per_gpu_batch": B, "global_batch": B * world, "sharding": "independent trajectories per rank, no per-step collective",
                        "l2": "inputs larger than L2 (activations are GBs per layer)", "precision": args.precision,
                        "tcgen05": not args.no_tcgen05, "micro_batch": args.micro_batch or None},
-            "clocks": sampler.summary(), "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "rollout": rollout,
+            "clocks": sampler.summary(), "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "rollout": rollout, "gather": gather,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
