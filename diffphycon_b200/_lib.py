@@ -58,7 +58,8 @@ _SIGNATURES = {
     "dpc_conv3d_tcgen05": ([C.POINTER(ConvParams), c_fp], C.c_int),
     "dpc_groupnorm_silu": ([c_fp, c_fp, c_fp, c_fp, c_fp, C.c_int64, C.c_int64, c_fp, c_fp, C.c_int32, C.c_int64,
                             C.c_int32, C.c_int32, C.c_float, c_fp], C.c_int),
-    "dpc_layernorm_channels": ([c_fp, c_fp, c_fp, C.c_int64, C.c_int32, C.c_float, c_fp], C.c_int),
+    "dpc_layernorm_channels": ([c_fp, c_fp, c_fp, c_fp, C.c_int64, C.c_int32, C.c_float, C.c_int32, c_fp], C.c_int),
+    "dpc_upsample_nearest2x": ([c_fp, c_fp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_pack_input": ([c_fp, c_fp] + [C.c_int32] * 8 + [c_fp], C.c_int),
     "dpc_temporal_attention": ([c_fp] * 5 + [C.c_int32] * 6 + [c_fp], C.c_int),
     "dpc_spatial_attention": ([c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
@@ -191,9 +192,15 @@ def groupnorm_silu(y, stats, gamma, beta, scale_shift, ss_stride, ss_off, residu
 
 
 @_timed("layernorm_channels")
-def layernorm_channels(x, gamma, out, rows, Cn, eps=1e-5):
-    check(lib().dpc_layernorm_channels(ptr(x), ptr(gamma), ptr(out), rows, Cn, eps, stream_ptr()),
-          "dpc_layernorm_channels")
+def layernorm_channels(x, gamma, out, rows, Cn, eps=1e-5, residual=None, use_rsqrt=False):
+    check(lib().dpc_layernorm_channels(ptr(x), ptr(gamma), ptr(residual), ptr(out), rows, Cn, eps, 1 if use_rsqrt else 0,
+                                       stream_ptr()), "dpc_layernorm_channels")
+    LaunchCounter.count += 1
+
+
+@_timed("upsample_nearest2x")
+def upsample_nearest2x(x, out, BF, H, W, Cn):
+    check(lib().dpc_upsample_nearest2x(ptr(x), ptr(out), BF, H, W, Cn, stream_ptr()), "dpc_upsample_nearest2x")
     LaunchCounter.count += 1
 
 

@@ -101,8 +101,8 @@ groupnorm_silu_kernel(const float* __restrict__ y, const double* __restrict__ st
 // one warp per row; two-pass moments in registers (matches torch.var(unbiased=False) / torch.mean)
 template <int MAXV>
 __global__ void __launch_bounds__(256)
-layernorm_channels_kernel(const float* __restrict__ x, const float* __restrict__ gamma, float* __restrict__ out,
-                          int64_t rows, int C, float eps) {
+layernorm_channels_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ residual,
+                          float* __restrict__ out, int64_t rows, int C, float eps, int use_rsqrt) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -133,11 +133,18 @@ layernorm_channels_kernel(const float* __restrict__ x, const float* __restrict__
     }
     const float var = warp_sum(q) * invC;
     const float den = sqrtf(var + eps);
+    const float rden = __fdiv_rn(1.0f, den);     // (var + eps).rsqrt() of the 2-D LayerNorm variants
     float* orow = out + (size_t)r * C;
+    const float* rrow = residual ? residual + (size_t)r * C : nullptr;
 #pragma unroll
     for (int j = 0; j < MAXV; ++j) {
       int c = lane + 32 * j;
-      if (c < C) orow[c] = __fmul_rn(__fdiv_rn(__fsub_rn(v[j], mean), den), gam[j]);
+      if (c < C) {
+        const float d = __fsub_rn(v[j], mean);
+        float o = use_rsqrt ? __fmul_rn(__fmul_rn(d, rden), gam[j]) : __fmul_rn(__fdiv_rn(d, den), gam[j]);
+        if (rrow) o = __fadd_rn(o, rrow[c]);
+        orow[c] = o;
+      }
     }
   }
 }
@@ -162,7 +169,34 @@ pack_input_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t 
   }
 }
 
+// nearest-neighbour 2x upsampling in H and W, channels-last rows (nn.Upsample(scale_factor=2, mode='nearest'),
+// model/burgers_1d/unet.py:40-44)
+__global__ void __launch_bounds__(256)
+upsample_nearest2x_kernel(const float4* __restrict__ x, float4* __restrict__ out, int64_t BF, int H, int W, int C4) {
+  const int64_t total = BF * (2 * H) * (2 * W) * C4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4);
+    int64_t r = i / C4;
+    const int wo = (int)(r % (2 * W)); r /= (2 * W);
+    const int ho = (int)(r % (2 * H));
+    const int64_t bf = r / (2 * H);
+    out[i] = x[((bf * H + (ho >> 1)) * W + (wo >> 1)) * C4 + c];
+  }
+}
+
 }  // namespace dpc
+
+extern "C" int dpc_upsample_nearest2x(const float* x, float* out, int64_t BF, int32_t H, int32_t W, int32_t C, void* stream) {
+  using namespace dpc;
+  DPC_CHECK_ARG(x && out && BF > 0 && H > 0 && W > 0 && C > 0 && C % 4 == 0);
+  const int64_t total = BF * 4 * H * W * (C / 4);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  upsample_nearest2x_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(x),
+                                                                                reinterpret_cast<float4*>(out), BF, H, W, C / 4);
+  DPC_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int dpc_groupnorm_silu(const float* y, const double* stats, const float* gamma, const float* beta,
                                   const float* scale_shift, int64_t ss_stride, int64_t ss_off, const float* residual,
@@ -190,8 +224,8 @@ extern "C" int dpc_groupnorm_silu(const float* y, const double* stats, const flo
   return 0;
 }
 
-extern "C" int dpc_layernorm_channels(const float* x, const float* gamma, float* out, int64_t rows, int32_t C,
-                                      float eps, void* stream) {
+extern "C" int dpc_layernorm_channels(const float* x, const float* gamma, const float* residual, float* out, int64_t rows,
+                                      int32_t C, float eps, int32_t use_rsqrt, void* stream) {
   using namespace dpc;
   DPC_CHECK_ARG(x && gamma && out && rows > 0 && C > 0 && C <= 512);
   int64_t warps_needed = rows;
@@ -200,13 +234,13 @@ extern "C" int dpc_layernorm_channels(const float* x, const float* gamma, float*
   if (blocks > cap) blocks = cap;
   cudaStream_t st = (cudaStream_t)stream;
   if (C <= 64)
-    layernorm_channels_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, out, rows, C, eps);
+    layernorm_channels_kernel<2><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, residual, out, rows, C, eps, use_rsqrt);
   else if (C <= 128)
-    layernorm_channels_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, out, rows, C, eps);
+    layernorm_channels_kernel<4><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, residual, out, rows, C, eps, use_rsqrt);
   else if (C <= 256)
-    layernorm_channels_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, out, rows, C, eps);
+    layernorm_channels_kernel<8><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, residual, out, rows, C, eps, use_rsqrt);
   else
-    layernorm_channels_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, out, rows, C, eps);
+    layernorm_channels_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(x, gamma, residual, out, rows, C, eps, use_rsqrt);
   DPC_LAUNCH_CHECK();
   return 0;
 }

@@ -93,9 +93,14 @@ int dpc_groupnorm_silu(const float* y, const double* stats, const float* gamma, 
                        const float* residual, float* out,
                        int32_t B, int64_t rows_per_sample, int32_t C, int32_t groups, float eps, void* stream);
 
-/* Channel LayerNorm, gain only: (x-mean)/sqrt(var+eps)*gamma over C for every row — conv3d.py:165-174. */
-int dpc_layernorm_channels(const float* x, const float* gamma, float* out, int64_t rows, int32_t C, float eps,
-                           void* stream);
+/* Channel LayerNorm, gain only, over C for every row (+ optional residual added after the gain):
+ * use_rsqrt 0: (x-mean)/sqrt(var+eps)*gamma  — conv3d.py:165-174;
+ * use_rsqrt 1: (x-mean)*rsqrt(var+eps)*gamma — the 2-D variants, model/burgers_1d/unet.py:60-70. */
+int dpc_layernorm_channels(const float* x, const float* gamma, const float* residual, float* out, int64_t rows,
+                           int32_t C, float eps, int32_t use_rsqrt, void* stream);
+
+/* nn.Upsample(scale_factor=2, mode='nearest') on channels-last [BF,H,W,C] -> [BF,2H,2W,C] (model/burgers_1d/unet.py:40-44). */
+int dpc_upsample_nearest2x(const float* x, float* out, int64_t BF, int32_t H, int32_t W, int32_t C, void* stream);
 
 /* Reference layout [B,F,Ctot,H,W], channels [c0, c0+Cin) -> channels-last [B,F,H,W,Cpad] zero padded
  * (replaces the permute at conv3d.py:495 and the slice x[:, :, 3:5] at smoke.py:612). */

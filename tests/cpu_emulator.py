@@ -92,11 +92,20 @@ def groupnorm_silu(y, stats, gamma, beta, scale_shift, ss_stride, ss_off, residu
     out[: B * rps * Cn] = t.reshape(-1)
 
 
-def layernorm_channels(x, gamma, out, rows, Cn, eps=1e-5):
+def layernorm_channels(x, gamma, out, rows, Cn, eps=1e-5, residual=None, use_rsqrt=False):
     v = x[: rows * Cn].reshape(rows, Cn)
     mean = v.mean(dim=1, keepdim=True)
     var = v.var(dim=1, unbiased=False, keepdim=True)
-    out[: rows * Cn] = ((v - mean) / (var + eps).sqrt() * gamma).reshape(-1)
+    o = (v - mean) * (var + eps).rsqrt() * gamma if use_rsqrt else (v - mean) / (var + eps).sqrt() * gamma
+    if residual is not None:
+        o = o + residual[: rows * Cn].reshape(rows, Cn)
+    out[: rows * Cn] = o.reshape(-1)
+
+
+def upsample_nearest2x(x, out, BF, H, W, Cn):
+    v = x[: BF * H * W * Cn].reshape(BF, H, W, Cn)
+    o = v.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2)
+    out[: o.numel()] = o.reshape(-1)
 
 
 def pack_input(x, out, B, F, Ctot, c0, Cin, H, W, Cpad):
@@ -203,12 +212,14 @@ def guided_step(ddim, x, eps_joint, eps_w, noise, init, g, c, x_out, x_start_out
         x_start_out.copy_(xs)
 
 
+EMULATED = ("conv", "groupnorm_silu", "layernorm_channels", "pack_input", "temporal_attention", "spatial_attention",
+            "spatial_linear_attention", "time_embed", "time_proj", "predict_x_start", "guided_step", "upsample_nearest2x")
+
+
 def install_raw():
     """Same as install() without pytest (used inside spawned worker processes)."""
     from diffphycon_b200 import _lib, unet3d
-    for name in ("conv", "groupnorm_silu", "layernorm_channels", "pack_input", "temporal_attention",
-                 "spatial_attention", "spatial_linear_attention", "time_embed", "time_proj", "predict_x_start",
-                 "guided_step"):
+    for name in EMULATED:
         setattr(_lib, name, globals()[name])
     _lib.stream_ptr = lambda: None
     unet3d._require_cuda = lambda x: None
@@ -217,9 +228,7 @@ def install_raw():
 def install(monkeypatch):
     """Route diffphycon_b200._lib's launch wrappers to the emulators above (tests only)."""
     from diffphycon_b200 import _lib
-    for name in ("conv", "groupnorm_silu", "layernorm_channels", "pack_input", "temporal_attention",
-                 "spatial_attention", "spatial_linear_attention", "time_embed", "time_proj", "predict_x_start",
-                 "guided_step"):
+    for name in EMULATED:
         monkeypatch.setattr(_lib, name, globals()[name])
     monkeypatch.setattr(_lib, "stream_ptr", lambda: None)
 
