@@ -71,6 +71,8 @@ _SIGNATURES = {
     "dpc_ddim_guided_step": ([c_fp] * 6 + [C.c_int32, C.POINTER(StepCoefs), c_fp, c_fp] + [C.c_int32] * 4 + [c_fp],
                              C.c_int),
     "dpc_predict_x_start": ([c_fp, c_fp, C.c_float, C.c_float, C.c_int32, c_fp, C.c_int64, c_fp], C.c_int),
+    "dpc_burgers_model_output": ([c_fp] * 5 + [C.c_int32] + [C.c_float] * 4 + [C.c_int32, C.c_int64, C.c_int64, c_fp], C.c_int),
+    "dpc_ddpm_posterior_step": ([c_fp] * 7 + [C.c_float] * 3 + [C.c_int32] + [C.c_float] * 3 + [C.c_int64, c_fp], C.c_int),
     "dpc_burgers_rollout": ([c_fp] * 3 + [C.c_int32] * 4 + [C.c_float] * 6 + [c_fp], C.c_int),
     "dpc_smoke_rollout": ([c_fp] * 14 + [C.c_int32] * 4 + [C.c_double, C.c_double, C.c_int32, c_fp], C.c_int),
 }
@@ -272,4 +274,19 @@ def smoke_rollout(fluid_mask, velocity_mask, init_velocity, init_density, c1, c2
 def burgers_rollout(u0, f, traj, N, s, Nt, steps, t0, t1, d0, d1, d2, dt):
     check(lib().dpc_burgers_rollout(ptr(u0), ptr(f), ptr(traj), N, s, Nt, steps, t0, t1, d0, d1, d2, dt, stream_ptr()),
           "dpc_burgers_rollout")
+    LaunchCounter.count += 1
+
+
+@_timed("burgers_model_output")
+def burgers_model_output(x, eps1, eps2, out, x_start, mode, coef, beta, sr, srm1, Cn, plane):
+    check(lib().dpc_burgers_model_output(ptr(x), ptr(eps1), ptr(eps2), ptr(out), ptr(x_start), mode, coef, beta, sr, srm1, Cn,
+                                         plane, x.numel(), stream_ptr()), "dpc_burgers_model_output")
+    LaunchCounter.count += 1
+
+
+@_timed("ddpm_posterior_step")
+def ddpm_posterior_step(x, eps, g, noise, x_out, x_start_out, pred_noise_out, gscale, sr, srm1, clip, c1, c2, sigma):
+    check(lib().dpc_ddpm_posterior_step(ptr(x), ptr(eps), ptr(g), ptr(noise), ptr(x_out), ptr(x_start_out), ptr(pred_noise_out),
+                                        gscale, sr, srm1, 1 if clip else 0, c1, c2, sigma, x.numel(), stream_ptr()),
+          "dpc_ddpm_posterior_step")
     LaunchCounter.count += 1

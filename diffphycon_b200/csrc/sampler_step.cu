@@ -195,3 +195,78 @@ extern "C" int dpc_predict_x_start(const float* x, const float* eps, float sqrt_
   DPC_LAUNCH_CHECK();
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Burgers sampler (diffusion/diffusion_1d_burgers.py:396-470): two-model prior re-weighting + x0 prediction, and the
+// guided posterior step.  Same conventions as above: explicit round-to-nearest ops in the reference's evaluation order.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace dpc {
+
+// mode 0: out = eps1 - coef*eps2' ; mode 1: out = (eps1 - coef*eps2') / beta ; mode 2: out = (beta*eps1)'
+// (' = channel 0 zeroed, diffusion_1d_burgers.py:403, :414);  x_start = sr*x - srm1*out
+__global__ void __launch_bounds__(256)
+burgers_model_output_kernel(const float* __restrict__ x, const float* __restrict__ eps1, const float* __restrict__ eps2,
+                            float* __restrict__ out, float* __restrict__ x_start, int mode, float coef, float beta, float sr,
+                            float srm1, int C, int64_t plane, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)((i / plane) % C);
+    float o;
+    if (mode == 2) {
+      o = (c == 0) ? 0.0f : __fmul_rn(beta, eps1[i]);
+    } else {
+      const float e2 = (c == 0) ? 0.0f : eps2[i];
+      o = __fsub_rn(eps1[i], __fmul_rn(coef, e2));
+      if (mode == 1) o = __fdiv_rn(o, beta);
+    }
+    out[i] = o;
+    if (x_start) x_start[i] = __fsub_rn(__fmul_rn(sr, x[i]), __fmul_rn(srm1, o));
+  }
+}
+
+// pred_noise = eps (+ g*gscale); x_start = [clamp](sr*x - srm1*pred_noise); x_{t-1} = c1*x_start + c2*x (+ sigma*noise)
+__global__ void __launch_bounds__(256)
+ddpm_posterior_step_kernel(const float* __restrict__ x, const float* __restrict__ eps, const float* __restrict__ g,
+                           const float* __restrict__ noise, float* __restrict__ x_out, float* __restrict__ x_start_out,
+                           float* __restrict__ pred_noise_out, float gscale, float sr, float srm1, int clip, float c1,
+                           float c2, float sigma, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float pn = eps[i];
+    if (g) pn = __fadd_rn(pn, __fmul_rn(g[i], gscale));
+    float xs = __fsub_rn(__fmul_rn(sr, x[i]), __fmul_rn(srm1, pn));
+    if (clip) xs = fminf(fmaxf(xs, -1.0f), 1.0f);
+    const float mean = __fadd_rn(__fmul_rn(c1, xs), __fmul_rn(c2, x[i]));
+    x_out[i] = noise ? __fadd_rn(mean, __fmul_rn(sigma, noise[i])) : mean;
+    if (x_start_out) x_start_out[i] = xs;
+    if (pred_noise_out) pred_noise_out[i] = pn;
+  }
+}
+
+}  // namespace dpc
+
+extern "C" int dpc_burgers_model_output(const float* x, const float* eps1, const float* eps2, float* out, float* x_start,
+                                        int32_t mode, float coef, float beta, float sqrt_recip, float sqrt_recipm1, int32_t C,
+                                        int64_t plane, int64_t n, void* stream) {
+  using namespace dpc;
+  DPC_CHECK_ARG(x && eps1 && out && n > 0 && C > 0 && plane > 0 && mode >= 0 && mode <= 2 && (mode == 2 || eps2));
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  burgers_model_output_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, eps1, eps2, out, x_start, mode, coef, beta,
+                                                                                  sqrt_recip, sqrt_recipm1, C, plane, n);
+  DPC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dpc_ddpm_posterior_step(const float* x, const float* eps, const float* g, const float* noise, float* x_out,
+                                       float* x_start_out, float* pred_noise_out, float gscale, float sqrt_recip,
+                                       float sqrt_recipm1, int32_t clip, float coef1, float coef2, float sigma, int64_t n,
+                                       void* stream) {
+  using namespace dpc;
+  DPC_CHECK_ARG(x && eps && x_out && n > 0);
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  ddpm_posterior_step_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, eps, g, noise, x_out, x_start_out,
+                                                                                 pred_noise_out, gscale, sqrt_recip, sqrt_recipm1,
+                                                                                 clip, coef1, coef2, sigma, n);
+  DPC_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,322 @@
+"""B200-native `GaussianDiffusion` for the Burgers task — drop-in for diffusion/diffusion_1d_burgers.py:192-690 (cited
+as burgers.py:line) on the sampling path the reference's inference uses (inference/inference_1d_burgers.py:261-305):
+2-D conv models over (time, space), optional two-model prior re-weighting (`eval_two_models`, `prior_beta`,
+`w_scheduler`), u0 / uT conditioning, guidance through a user `nablaJ` callable (`get_nablaJ`) with `J_scheduler`, DDPM
+posterior.  Also the guidance helpers callers import from the same module (`get_nablaJ`, the schedulers).
+Network forwards run on the kernels behind `Unet2D`; the elementwise sampler math is two fused kernels per step
+(`dpc_burgers_model_output`, `dpc_ddpm_posterior_step`).  Options the released inference never enables (DDIM,
+residual conditioning, recurrence, 1-D conv models, self-conditioning) raise NotImplementedError."""
+from __future__ import annotations
+
+import math
+from collections import namedtuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import _lib
+
+ModelPrediction = namedtuple('ModelPrediction', ['pred_noise', 'pred_x_start'])
+
+
+# ---- guidance helpers (burgers.py:34-111) ------------------------------------------------------------------------
+def get_nablaJ(loss_fn):
+    """burgers.py:34-49: gradient of a per-sample loss w.r.t. the (state, control) tensor."""
+    def nablaJ(x):
+        with torch.enable_grad():
+            x = x.detach().requires_grad_(True)
+            J = loss_fn(x)
+            grad = torch.autograd.grad(J, x, grad_outputs=torch.ones_like(J), allow_unused=True)[0]
+        return grad.detach()
+    return nablaJ
+
+
+def _cosine_betas(timesteps, s=0.008):
+    steps = timesteps + 1
+    x = torch.linspace(0, timesteps, steps, dtype=torch.float64)
+    ac = torch.cos(((x / timesteps) + s) / (1 + s) * math.pi * 0.5) ** 2
+    ac = ac / ac[0]
+    return torch.clip(1 - (ac[1:] / ac[:-1]), 0, 0.999)
+
+
+def cosine_beta_J_schedule(t, s=0.008):
+    """burgers.py:71-82 (1000 steps hard-coded)."""
+    return _cosine_betas(1000, s)[t]
+
+
+def sigmoid_schedule(t, start=-3, end=3, tau=1, clamp_min=1e-5):
+    """burgers.py:94-108."""
+    timesteps = 1000
+    x = torch.linspace(0, timesteps, timesteps + 1, dtype=torch.float64) / timesteps
+    v_start = torch.tensor(start / tau).sigmoid()
+    v_end = torch.tensor(end / tau).sigmoid()
+    ac = (-((x * (end - start) + start) / tau).sigmoid() + v_end) / (v_end - v_start)
+    ac = ac / ac[0]
+    return torch.clip(1 - (ac[1:] / ac[:-1]), 0, 0.999)[t]
+
+
+def sigmoid_schedule_flip(t):
+    return sigmoid_schedule(999 - t)
+
+
+def linear_beta_schedule(timesteps):
+    scale = 1000 / timesteps
+    return torch.linspace(scale * 0.0001, scale * 0.02, timesteps, dtype=torch.float64)
+
+
+def cosine_beta_schedule(timesteps, s=0.008):
+    return _cosine_betas(timesteps, s)
+
+
+def normalize_to_neg_one_to_one(img):
+    return img * 2 - 1
+
+
+def unnormalize_to_zero_to_one(t):
+    return (t + 1) * 0.5
+
+
+def identity(t, *args, **kwargs):
+    return t
+
+
+class GaussianDiffusion(nn.Module):
+    """Constructor: burgers.py:193-225."""
+
+    def __init__(self, model, *, seq_length, timesteps=1000, sampling_timesteps=None, objective='pred_noise',
+                 beta_schedule='cosine', ddim_sampling_eta=0., auto_normalize=True, guidance_u0=True, temporal=False,
+                 use_conv2d=False, is_condition_u0=False, is_condition_uT=False, is_condition_u0_zero_pred_noise=True,
+                 is_condition_uT_zero_pred_noise=True, train_on_partially_observed=None,
+                 set_unobserved_to_zero_during_sampling=False, conditioned_on_residual=None, residual_on_u0=False,
+                 recurrence=False, recurrence_k=1, is_model_w=False, eval_two_models=False, expand_condition=False,
+                 prior_beta=1, normalize_beta=False, train_on_padded_locations=True, condition_idx=10):
+        super().__init__()
+        if not (temporal and use_conv2d):
+            raise NotImplementedError("only the (time, space) 2-D conv models of the released Burgers runs are implemented")
+        if conditioned_on_residual is not None or recurrence or expand_condition or objective != 'pred_noise':
+            raise NotImplementedError("option unused by the released Burgers inference")
+        if not eval_two_models:
+            self.model = model
+            self.channels = self.model.channels
+            self.self_condition = self.model.self_condition
+        else:
+            self.model_uw, self.model_w = model[0], model[1]
+            self.channels = self.model_uw.channels
+            self.self_condition = self.model_uw.self_condition
+        assert type(seq_length) is tuple and len(seq_length) == 2, "should be a tuple of (Nt, Nx)"
+        self.temporal, self.conv2d, self.traj_size = True, True, seq_length
+        self.objective = objective
+        if beta_schedule == 'linear':
+            betas = linear_beta_schedule(timesteps)
+        elif beta_schedule == 'cosine':
+            betas = cosine_beta_schedule(timesteps)
+        else:
+            raise ValueError(f'unknown beta schedule {beta_schedule}')
+        alphas = 1. - betas
+        alphas_prev = F.pad(alphas[:-1], (1, 0), value=1.)
+        alphas_cumprod = torch.cumprod(alphas, dim=0)
+        alphas_cumprod_prev = F.pad(alphas_cumprod[:-1], (1, 0), value=1.)
+        timesteps, = betas.shape
+        self.num_timesteps = int(timesteps)
+        self.sampling_timesteps = timesteps if sampling_timesteps is None else sampling_timesteps
+        assert self.sampling_timesteps <= timesteps
+        self.is_ddim_sampling = self.sampling_timesteps < timesteps
+        self.ddim_sampling_eta = ddim_sampling_eta
+
+        def register_buffer(name, val):
+            self.register_buffer(name, val.to(torch.float32))
+
+        register_buffer('betas', betas)
+        self.alphas = alphas.to(torch.float32).clone()
+        self.alphas_prev = alphas_prev.to(torch.float32).clone()
+        register_buffer('alphas_cumprod', alphas_cumprod)
+        register_buffer('alphas_cumprod_prev', alphas_cumprod_prev)
+        register_buffer('sqrt_alphas_cumprod', torch.sqrt(alphas_cumprod))
+        register_buffer('sqrt_one_minus_alphas_cumprod', torch.sqrt(1. - alphas_cumprod))
+        register_buffer('log_one_minus_alphas_cumprod', torch.log(1. - alphas_cumprod))
+        register_buffer('sqrt_recip_alphas_cumprod', torch.sqrt(1. / alphas_cumprod))
+        register_buffer('sqrt_recipm1_alphas_cumprod', torch.sqrt(1. / alphas_cumprod - 1))
+        posterior_variance = betas * (1. - alphas_cumprod_prev) / (1. - alphas_cumprod)
+        register_buffer('posterior_variance', posterior_variance)
+        register_buffer('posterior_log_variance_clipped', torch.log(posterior_variance.clamp(min=1e-20)))
+        register_buffer('posterior_mean_coef1', betas * torch.sqrt(alphas_cumprod_prev) / (1. - alphas_cumprod))
+        register_buffer('posterior_mean_coef2', (1. - alphas_cumprod_prev) * torch.sqrt(alphas) / (1. - alphas_cumprod))
+        register_buffer('loss_weight', torch.ones_like(alphas_cumprod / (1 - alphas_cumprod)))
+        self.normalize = normalize_to_neg_one_to_one if auto_normalize else identity
+        self.unnormalize = unnormalize_to_zero_to_one if auto_normalize else identity
+        self.guidance_u0 = guidance_u0
+        self.is_condition_u0, self.is_condition_uT = is_condition_u0, is_condition_uT
+        self.is_condition_u0_zero_pred_noise = is_condition_u0_zero_pred_noise
+        self.is_condition_uT_zero_pred_noise = is_condition_uT_zero_pred_noise
+        self.train_on_partially_observed = train_on_partially_observed
+        self.set_unobserved_to_zero_during_sampling = set_unobserved_to_zero_during_sampling
+        self.conditioned_on_residual = None
+        self.residual_on_u0 = residual_on_u0
+        self.recurrence, self.recurrence_k = False, recurrence_k
+        self.is_model_w = is_model_w
+        self.eval_two_models = eval_two_models
+        self.expand_condition = False
+        self.prior_beta = prior_beta
+        self.train_on_padded_locations = train_on_padded_locations
+        self.normalize_beta = normalize_beta
+        self.condition_idx = condition_idx
+        self.progress = False
+        self._host_sched = None
+
+    def _sched(self):
+        if self._host_sched is None:
+            names = ('sqrt_recip_alphas_cumprod', 'sqrt_recipm1_alphas_cumprod', 'posterior_log_variance_clipped',
+                     'posterior_mean_coef1', 'posterior_mean_coef2')
+            self._host_sched = {n: getattr(self, n).detach().float().cpu() for n in names}
+        return self._host_sched
+
+    def _apply(self, fn, *a, **k):
+        self._host_sched = None
+        return super()._apply(fn, *a, **k)
+
+    def sample_noise(self, shape, device):
+        return torch.randn(shape, device=device)
+
+    @staticmethod
+    def _f32(v) -> float:
+        """A python / 0-dim-tensor scalar as the float32 value PyTorch would multiply a float32 tensor with."""
+        return float(torch.as_tensor(v, dtype=torch.float64).to(torch.float32))
+
+    # ---- burgers.py:396-450 -----------------------------------------------------------------------------------
+    def model_predictions(self, x, t, x_self_cond=None, residual=None, clip_x_start=False, rederive_pred_noise=False, **kwargs):
+        """Returns (pred_noise, x_start) like the reference; `t` is the batched time tensor, all entries equal."""
+        ti = int(t[0].item()) if torch.is_tensor(t) else int(t)
+        return self._predict(x.contiguous(), ti, clip_x_start, **kwargs)[:2]
+
+    def _model_output(self, x, ti, **kwargs):
+        b = x.shape[0]
+        tt = torch.full((b,), ti, device=x.device, dtype=torch.long)
+        s = self._sched()
+        sr, srm1 = float(s['sqrt_recip_alphas_cumprod'][ti]), float(s['sqrt_recipm1_alphas_cumprod'][ti])
+        plane = x.shape[-1] * x.shape[-2]
+        out, xs0 = torch.empty_like(x), torch.empty_like(x)
+        if self.eval_two_models:
+            eps_uw = self.model_uw(x, tt)
+            x_w = x.clone()
+            x_w[..., 0, 1:self.condition_idx, :] = 0          # burgers.py:400-401
+            eps_w = self.model_w(x_w, tt)
+            ws = kwargs.get('w_scheduler')
+            eta = ws(ti) if ws is not None else 1
+            if self.normalize_beta:
+                _lib.burgers_model_output(x, eps_uw, eps_w, out, xs0, 1, self._f32(1 - self.prior_beta),
+                                          self._f32(self.prior_beta), sr, srm1, self.channels, plane)
+            else:
+                _lib.burgers_model_output(x, eps_uw, eps_w, out, xs0, 0, self._f32((1 - self.prior_beta) * eta), 1.0, sr, srm1,
+                                          self.channels, plane)
+        elif self.is_model_w:
+            x[..., 0, 1:self.condition_idx, :] = 0             # in place, like burgers.py:412
+            eps = self.model(x, tt)
+            _lib.burgers_model_output(x, eps, None, out, xs0, 2, 0.0, self._f32(self.prior_beta), sr, srm1, self.channels, plane)
+        else:
+            out = self.model(x, tt)
+            xs0 = None
+        return out, xs0, sr, srm1
+
+    def _predict(self, x, ti, clip_x_start=False, clip_denoised=None, noise=None, posterior=False, **kwargs):
+        """model_predictions (+ p_mean_variance / posterior when `posterior`)."""
+        nablaJ = kwargs.get('nablaJ')
+        Js = kwargs.get('J_scheduler')
+        proj = kwargs.get('proj_guidance')
+        if kwargs.get('pred_noise') is not None:
+            assert self.guidance_u0 is False, 'guidance should be w.r.t. ut'
+            eps = kwargs['pred_noise'].contiguous()
+            s = self._sched()
+            sr, srm1 = float(s['sqrt_recip_alphas_cumprod'][ti]), float(s['sqrt_recipm1_alphas_cumprod'][ti])
+            xs0 = None
+        else:
+            eps, xs0, sr, srm1 = self._model_output(x, ti, **kwargs)
+        g, gscale = None, 1.0
+        if self.guidance_u0 and nablaJ is not None:
+            if xs0 is None or clip_x_start:
+                xs0 = torch.empty_like(x)
+                _lib.predict_x_start(x, eps, sr, srm1, clip_x_start, xs0)
+            gj = nablaJ(xs0.detach())
+            sc = Js(ti) if Js is not None else 1.
+            if proj is not None:
+                eps = proj(eps, gj * sc).contiguous()     # user post-processing of the guidance (burgers.py:52-68)
+            elif torch.is_tensor(gj):
+                g, gscale = gj.float().contiguous(), self._f32(sc)
+        s = self._sched()
+        pred, x_start, pred_noise = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+        if posterior:
+            c1, c2 = float(s['posterior_mean_coef1'][ti]), float(s['posterior_mean_coef2'][ti])
+            sigma = float((0.5 * s['posterior_log_variance_clipped'][ti]).exp())
+            _lib.ddpm_posterior_step(x, eps, g, noise, pred, x_start, pred_noise, gscale, sr, srm1,
+                                     bool(clip_denoised) or clip_x_start, c1, c2, sigma)
+        else:
+            _lib.ddpm_posterior_step(x, eps, g, None, pred, x_start, pred_noise, gscale, sr, srm1, clip_x_start, 0.0, 0.0, 0.0)
+        return pred_noise, x_start, pred
+
+    # ---- burgers.py:464-470 -----------------------------------------------------------------------------------
+    def p_sample(self, x, t: int, x_self_cond=None, residual=None, **kwargs):
+        x = x.contiguous()
+        noise = self.sample_noise(x.shape, x.device) if t > 0 else None
+        kw = dict(kwargs)
+        clip = kw.pop('clip_denoised')
+        pred_noise, x_start, pred = self._predict(x, t, False, clip_denoised=clip, noise=noise, posterior=True, **kw)
+        return pred, x_start, pred_noise
+
+    def set_condition(self, img, u, shape, u0_or_uT):
+        """burgers.py:500-522 (4-D samples, no expand_condition)."""
+        assert len(shape) == 4
+        if u0_or_uT == 'uT':
+            img[:, 0, self.condition_idx, :] = u
+        elif u0_or_uT == 'u0':
+            img[:, 0, 0, :] = u
+        else:
+            assert False
+
+    # ---- burgers.py:525-584 (like the reference, NOT under no_grad: user nablaJ callables differentiate) ----------
+    def p_sample_loop(self, shape, **kwargs):
+        assert not self.is_ddim_sampling, 'wrong branch!'
+        nablaJ = kwargs.get('nablaJ')
+        Js = kwargs.get('J_scheduler')
+        proj = kwargs.get('proj_guidance')
+        device = self.betas.device
+        img = self.sample_noise(shape, device)
+        steps = reversed(range(0, self.num_timesteps))
+        if self.progress:
+            from tqdm.auto import tqdm
+            steps = tqdm(steps, desc='sampling loop time step', total=self.num_timesteps)
+        for t in steps:
+            if self.is_condition_u0:
+                self.set_condition(img, kwargs['u_init'].to(device), shape, 'u0')
+            if self.is_condition_uT:
+                self.set_condition(img, kwargs['u_final'].to(device), shape, 'uT')
+            if self.set_unobserved_to_zero_during_sampling:
+                Nx = img.size(-1)
+                img[:, 0, :, Nx // 4:(Nx * 3) // 4] = 0
+            img_curr, x_start, pred_noise = self.p_sample(img, t, None, residual=None, **kwargs)
+            if self.guidance_u0:
+                img = img_curr
+            else:
+                gj = nablaJ(img_curr) if nablaJ is not None else 0
+                sc = Js(t) if Js is not None else 1.
+                pn = proj(pred_noise, gj * sc) if proj is not None else pred_noise + gj * sc
+                kw = dict(kwargs)
+                kw['pred_noise'] = pn
+                img, x_start, _ = self.p_sample(img, t, None, residual=None, **kw)
+        return self.unnormalize(img)
+
+    def ddim_sample(self, shape, return_all_timesteps=False, **kwargs):
+        raise NotImplementedError("the released Burgers inference samples with DDPM (ddim asserts eval_two_models == False)")
+
+    def sample(self, batch_size=16, clip_denoised=True, **kwargs):
+        """burgers.py:646-690."""
+        if 'guidance_u0' in kwargs:
+            self.guidance_u0 = kwargs['guidance_u0']
+        if self.is_condition_u0:
+            assert 'is_condition_u0' not in kwargs, 'specify this value in the model. not during sampling.'
+            assert 'u_init' in kwargs and kwargs['u_init'] is not None
+        if self.is_condition_uT:
+            assert 'is_condition_uT' not in kwargs, 'specify this value in the model. not during sampling.'
+            assert 'u_final' in kwargs and kwargs['u_final'] is not None
+        sample_size = (batch_size, self.channels, *self.traj_size)
+        sample_fn = self.p_sample_loop if not self.is_ddim_sampling else self.ddim_sample
+        return sample_fn(sample_size, clip_denoised=clip_denoised, **kwargs)

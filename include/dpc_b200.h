@@ -192,6 +192,18 @@ int dpc_smoke_rollout(const int8_t* fluid_mask, const float* velocity_mask, cons
                       int32_t* iterations, int32_t B, int32_t nt, int32_t nx, int32_t T, double dt, double accuracy,
                       int32_t max_iterations, void* stream);
 
+/* Burgers sampler, elementwise parts of diffusion/diffusion_1d_burgers.py:396-470 on [B,C,H,W] tensors (n elements,
+ * `plane` = H*W): dpc_burgers_model_output combines the joint and prior network outputs (mode 0: eps1 - coef*eps2',
+ * mode 1: (eps1 - coef*eps2')/beta, mode 2: (beta*eps1)'; ' zeroes channel 0, :403, :414) and predicts x_start (:425);
+ * dpc_ddpm_posterior_step adds the guidance (eps + g*gscale, :431-434), re-predicts and optionally clamps x_start (:456-458)
+ * and applies the posterior (:381-389, :464-470).  g / noise / x_start_out / pred_noise_out may be NULL. */
+int dpc_burgers_model_output(const float* x, const float* eps1, const float* eps2, float* out, float* x_start, int32_t mode,
+                             float coef, float beta, float sqrt_recip, float sqrt_recipm1, int32_t C, int64_t plane,
+                             int64_t n, void* stream);
+int dpc_ddpm_posterior_step(const float* x, const float* eps, const float* g, const float* noise, float* x_out,
+                            float* x_start_out, float* pred_noise_out, float gscale, float sqrt_recip, float sqrt_recipm1,
+                            int32_t clip, float coef1, float coef2, float sigma, int64_t n, void* stream);
+
 /* Burgers finite-difference rollout — dataset/apps/generate_burgers.py:207-299 (burgers_numeric_solve_free), stencils
  * of Diff_mat_1D (:95-110).  u0 [N][s], f [N][Nt][s] -> traj [N][Nt+1][s] (u0 followed by one record per force window).
  * t0,t1 = -/+ 1/(2dx), d0,d1,d2 = visc*(1,-2,1)/dx^2 as fp32 (host: generate_burgers.py:255-258), steps = ceil(T/dt). */

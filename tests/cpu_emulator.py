@@ -212,7 +212,39 @@ def guided_step(ddim, x, eps_joint, eps_w, noise, init, g, c, x_out, x_start_out
         x_start_out.copy_(xs)
 
 
-EMULATED = ("conv", "groupnorm_silu", "layernorm_channels", "pack_input", "temporal_attention", "spatial_attention",
+def burgers_model_output(x, eps1, eps2, out, x_start, mode, coef, beta, sr, srm1, Cn, plane):
+    f32 = lambda v: torch.tensor(v, dtype=torch.float32)
+    if mode == 2:
+        o = f32(beta) * eps1
+        o[:, 0] = 0
+    else:
+        e2 = eps2.clone()
+        e2[:, 0] = 0
+        o = eps1 - f32(coef) * e2
+        if mode == 1:
+            o = o / f32(beta)
+    out.copy_(o)
+    if x_start is not None:
+        x_start.copy_(f32(sr) * x - f32(srm1) * o)
+
+
+def ddpm_posterior_step(x, eps, g, noise, x_out, x_start_out, pred_noise_out, gscale, sr, srm1, clip, c1, c2, sigma):
+    f32 = lambda v: torch.tensor(v, dtype=torch.float32)
+    pn = eps if g is None else eps + g * f32(gscale)
+    xs = f32(sr) * x - f32(srm1) * pn
+    if clip:
+        xs = xs.clamp(-1, 1)
+    o = f32(c1) * xs + f32(c2) * x
+    if noise is not None:
+        o = o + f32(sigma) * noise
+    x_out.copy_(o)
+    if x_start_out is not None:
+        x_start_out.copy_(xs)
+    if pred_noise_out is not None:
+        pred_noise_out.copy_(pn)
+
+
+EMULATED = ("burgers_model_output", "ddpm_posterior_step", "conv", "groupnorm_silu", "layernorm_channels", "pack_input", "temporal_attention", "spatial_attention",
             "spatial_linear_attention", "time_embed", "time_proj", "predict_x_start", "guided_step", "upsample_nearest2x")
 
 
