@@ -73,6 +73,9 @@ _SIGNATURES = {
     "dpc_predict_x_start": ([c_fp, c_fp, C.c_float, C.c_float, C.c_int32, c_fp, C.c_int64, c_fp], C.c_int),
     "dpc_burgers_model_output": ([c_fp] * 5 + [C.c_int32] + [C.c_float] * 4 + [C.c_int32, C.c_int64, C.c_int64, c_fp], C.c_int),
     "dpc_ddpm_posterior_step": ([c_fp] * 7 + [C.c_float] * 3 + [C.c_int32] + [C.c_float] * 3 + [C.c_int64, c_fp], C.c_int),
+    "dpc_jelly_x_start": ([c_fp] * 3 + [C.c_float] * 2 + [C.c_int32, C.c_int64, C.c_int64, c_fp], C.c_int),
+    "dpc_jelly_step": ([c_fp] * 12 + [C.c_float] * 5 + [C.c_int32] * 4 + [C.c_int64, c_fp], C.c_int),
+    "dpc_jelly_write_bd": ([c_fp] * 4 + [C.c_int32] * 3 + [C.c_int64, c_fp], C.c_int),
     "dpc_burgers_rollout": ([c_fp] * 3 + [C.c_int32] * 4 + [C.c_float] * 6 + [c_fp], C.c_int),
     "dpc_smoke_rollout": ([c_fp] * 14 + [C.c_int32] * 4 + [C.c_double, C.c_double, C.c_int32, c_fp], C.c_int),
 }
@@ -289,4 +292,31 @@ def ddpm_posterior_step(x, eps, g, noise, x_out, x_start_out, pred_noise_out, gs
     check(lib().dpc_ddpm_posterior_step(ptr(x), ptr(eps), ptr(g), ptr(noise), ptr(x_out), ptr(x_start_out), ptr(pred_noise_out),
                                         gscale, sr, srm1, 1 if clip else 0, c1, c2, sigma, x.numel(), stream_ptr()),
           "dpc_ddpm_posterior_step")
+    LaunchCounter.count += 1
+
+
+@_timed("jelly_x_start")
+def jelly_x_start(x, eps, x_start, sr, srm1, clip):
+    """x [B,F,7,H,W], eps / x_start [B,F,4,H,W]."""
+    B, F, _, H, W = x.shape
+    check(lib().dpc_jelly_x_start(ptr(x), ptr(eps), ptr(x_start), sr, srm1, 1 if clip else 0, B * F, H * W, stream_ptr()),
+          "dpc_jelly_x_start")
+    LaunchCounter.count += 1
+
+
+@_timed("jelly_step")
+def jelly_step(x, x_start, eps, eps_w, g, noise, state_0, thetas_0, x_next, x_w, dtheta, theta_mean, ga, gb, c1, c2, sigma,
+               ddim, cond_steps):
+    B, F, _, H, W = x.shape
+    check(lib().dpc_jelly_step(ptr(x), ptr(x_start), ptr(eps), ptr(eps_w), ptr(g), ptr(noise), ptr(state_0), ptr(thetas_0),
+                               ptr(x_next), ptr(x_w), ptr(dtheta), ptr(theta_mean), ga, gb, c1, c2, sigma, 1 if ddim else 0,
+                               B, F, cond_steps, H * W, stream_ptr()), "dpc_jelly_step")
+    LaunchCounter.count += 1
+
+
+@_timed("jelly_write_bd")
+def jelly_write_bd(pred_bd, bd_0, x_next, x_w, cond_steps):
+    B, F, _, H, W = x_next.shape
+    check(lib().dpc_jelly_write_bd(ptr(pred_bd), ptr(bd_0), ptr(x_next), ptr(x_w), B, F, cond_steps, H * W, stream_ptr()),
+          "dpc_jelly_write_bd")
     LaunchCounter.count += 1

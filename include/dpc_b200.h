@@ -204,6 +204,27 @@ int dpc_ddpm_posterior_step(const float* x, const float* eps, const float* g, co
                             float* x_start_out, float* pred_noise_out, float gscale, float sqrt_recip, float sqrt_recipm1,
                             int32_t clip, float coef1, float coef2, float sigma, int64_t n, void* stream);
 
+/* Jellyfish sampler step, diffusion/diffusion_2d_jellyfish.py (jf.py).  State x [B,F,7,H,W] = [state 3, boundary 3, theta 1],
+ * P = H*W; the diffused channels are {0,1,2,6}: eps / x_start / g / noise are [B,F,4,P], eps_w [B,F,1,P].
+ * dpc_jelly_x_start: x_start = clamp?(sqrt_recip*x4 - sqrt_recipm1*eps) (jf.py:714, :744, :764).
+ * dpc_jelly_step, one launch per sampling step: DDPM (ddim=0) pred = c1*x_start + c2*x4 + sigma*noise (jf.py:601-604, :789)
+ *   then pred -= ga*g - gb*eps_w with eps_w broadcast over the 4 channels (jf.py:798-804); DDIM (ddim=1) pred_noise = eps +
+ *   ga*g - gb*pad(eps_w) (eps_w on the theta channel only, jf.py:728-742), pred = c1*x_start + c2*pred_noise + sigma*noise
+ *   (jf.py:925-927).  Then dtheta[b,f] = mean_hw(theta) - thetas_0[b] (update_bd, jf.py:810-814), the conditions of
+ *   jf.py:858-864 (frames < cond_steps: state_0 and thetas_0; frames >= F-cond_steps: thetas_0), theta_mean [B,F] of the
+ *   conditioned theta (jf.py:876); writes channels 0..2 and 6 of x_next and channel 6 of x_w (the prior model's input).
+ *   g and noise may be NULL (no design_fn / t == 0); eps is read only when ddim=1.
+ * dpc_jelly_write_bd: channels 3..5 of x_next and x_w <- pred_bd [B*F,3,P], frames < cond_steps and >= F-cond_steps <- bd_0
+ *   [B,3,P] (jf.py:860-861). */
+int dpc_jelly_x_start(const float* x, const float* eps, float* x_start, float sqrt_recip, float sqrt_recipm1, int32_t clip,
+                      int64_t BF, int64_t P, void* stream);
+int dpc_jelly_step(const float* x, const float* x_start, const float* eps, const float* eps_w, const float* g,
+                   const float* noise, const float* state_0, const float* thetas_0, float* x_next, float* x_w, float* dtheta,
+                   float* theta_mean, float ga, float gb, float c1, float c2, float sigma, int32_t ddim, int32_t B, int32_t F,
+                   int32_t cond_steps, int64_t P, void* stream);
+int dpc_jelly_write_bd(const float* pred_bd, const float* bd_0, float* x_next, float* x_w, int32_t B, int32_t F,
+                       int32_t cond_steps, int64_t P, void* stream);
+
 /* Burgers finite-difference rollout — dataset/apps/generate_burgers.py:207-299 (burgers_numeric_solve_free), stencils
  * of Diff_mat_1D (:95-110).  u0 [N][s], f [N][Nt][s] -> traj [N][Nt+1][s] (u0 followed by one record per force window).
  * t0,t1 = -/+ 1/(2dx), d0,d1,d2 = visc*(1,-2,1)/dx^2 as fp32 (host: generate_burgers.py:255-258), steps = ceil(T/dt). */

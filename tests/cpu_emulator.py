@@ -244,7 +244,54 @@ def ddpm_posterior_step(x, eps, g, noise, x_out, x_start_out, pred_noise_out, gs
         pred_noise_out.copy_(pn)
 
 
-EMULATED = ("burgers_model_output", "ddpm_posterior_step", "conv", "groupnorm_silu", "layernorm_channels", "pack_input", "temporal_attention", "spatial_attention",
+def jelly_x_start(x, eps, x_start, sr, srm1, clip):
+    f32 = lambda v: torch.tensor(v, dtype=torch.float32)
+    x4 = torch.cat([x[:, :, :3], x[:, :, 6:]], dim=2)
+    xs = f32(sr) * x4 - f32(srm1) * eps
+    x_start.copy_(xs.clamp(-1, 1) if clip else xs)
+
+
+def jelly_step(x, x_start, eps, eps_w, g, noise, state_0, thetas_0, x_next, x_w, dtheta, theta_mean, ga, gb, c1, c2, sigma,
+               ddim, cond_steps):
+    f32 = lambda v: torch.tensor(v, dtype=torch.float32)
+    x4 = torch.cat([x[:, :, :3], x[:, :, 6:]], dim=2)
+    if ddim:
+        pn = eps
+        if g is not None:
+            pad = torch.zeros_like(eps)
+            pad[:, :, 3:] = eps_w
+            pn = eps + (f32(ga) * g - f32(gb) * pad)
+        pred = x_start * f32(c1) + f32(c2) * pn
+        if noise is not None:
+            pred = pred + f32(sigma) * noise
+    else:
+        pred = f32(c1) * x_start + f32(c2) * x4
+        if noise is not None:
+            pred = pred + f32(sigma) * noise
+        if g is not None:
+            pred = pred - (f32(ga) * g - f32(gb) * eps_w)
+    cs, th = cond_steps, thetas_0.reshape(-1, 1, 1, 1).expand(-1, 1, *x.shape[-2:])
+    theta = pred[:, :, 3].clone()
+    dtheta.copy_(theta.mean((-1, -2)) - thetas_0[:, None])
+    states = pred[:, :, :3].clone()
+    states[:, :cs] = state_0.unsqueeze(1)
+    theta[:, :cs] = th
+    theta[:, -cs:] = th
+    theta_mean.copy_(theta.mean((-1, -2)))
+    x_next[:, :, :3] = states
+    x_next[:, :, 6] = theta
+    x_w[:, :, 6] = theta
+
+
+def jelly_write_bd(pred_bd, bd_0, x_next, x_w, cond_steps):
+    bd = pred_bd.reshape(x_next.shape[0], x_next.shape[1], 3, *x_next.shape[-2:]).clone()
+    bd[:, :cond_steps] = bd_0.unsqueeze(1)
+    bd[:, -cond_steps:] = bd_0.unsqueeze(1)
+    x_next[:, :, 3:6] = bd
+    x_w[:, :, 3:6] = bd
+
+
+EMULATED = ("jelly_x_start", "jelly_step", "jelly_write_bd", "burgers_model_output", "ddpm_posterior_step", "conv", "groupnorm_silu", "layernorm_channels", "pack_input", "temporal_attention", "spatial_attention",
             "spatial_linear_attention", "time_embed", "time_proj", "predict_x_start", "guided_step", "upsample_nearest2x")
 
 

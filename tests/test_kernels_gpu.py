@@ -414,3 +414,36 @@ def test_linear_tcgen05(case):
                             cout=Cout, tcgen05=True)
     assert ran_tc, "shape should be served by the tcgen05 kernel"
     assert rel_err(y, ref) <= TOL_TF32
+
+
+@pytest.mark.parametrize("ddim", [False, True])
+@pytest.mark.parametrize("guided", [False, True])
+def test_jellyfish_step_kernels_match_torch_restatement(ddim, guided):
+    """dpc_jelly_x_start / dpc_jelly_step / dpc_jelly_write_bd against the torch restatement of jellyfish.py:744-806, :858-876
+    (tests/cpu_emulator.py, itself pinned to the reference traces in test_jellyfish_sampler.py): elementwise results
+    bit-exact, the theta means to 1e-6 (reduction order)."""
+    torch.manual_seed(11)
+    B, Fr, H, W, cs = 3, 5, 12, 20, 1
+    x = torch.randn(B, Fr, 7, H, W)
+    eps, eps_w = torch.randn(B, Fr, 4, H, W), torch.randn(B, Fr, 1, H, W)
+    g = torch.randn(B, Fr, 4, H, W) if guided else None
+    noise = torch.randn(B, Fr, 4, H, W)
+    state_0, bd_0, th0 = torch.randn(B, 3, H, W), torch.randn(B, 3, H, W), torch.rand(B)
+    pred_bd = torch.randn(B * Fr, 3, H, W)
+    sc = dict(ga=0.37, gb=0.21, c1=0.83, c2=0.41, sigma=0.6)
+    outs = {}
+    for where in ("cpu", "cuda"):
+        mod = emu if where == "cpu" else _lib
+        mv = lambda t: None if t is None else t.to(where)
+        xs = torch.empty(B, Fr, 4, H, W, device=where)
+        mod.jelly_x_start(mv(x), mv(eps), xs, 1.7, 0.9, True)
+        x_next, x_w = torch.zeros(B, Fr, 7, H, W, device=where), torch.zeros(B, Fr, 7, H, W, device=where)
+        dth, thm = torch.empty(B, Fr, device=where), torch.empty(B, Fr, device=where)
+        mod.jelly_step(mv(x), xs, mv(eps), mv(eps_w), mv(g), mv(noise), mv(state_0), mv(th0), x_next, x_w, dth, thm,
+                       sc["ga"], sc["gb"], sc["c1"], sc["c2"], sc["sigma"], ddim, cs)
+        mod.jelly_write_bd(mv(pred_bd), mv(bd_0), x_next, x_w, cs)
+        outs[where] = [t.cpu() for t in (xs, x_next, x_w, dth, thm)]
+    for a, b in zip(outs["cpu"][:3], outs["cuda"][:3]):
+        assert torch.equal(a, b)
+    for a, b in zip(outs["cpu"][3:], outs["cuda"][3:]):
+        assert (a - b).abs().max().item() <= 1e-6
