@@ -4,6 +4,12 @@ Public surface (mirrors the reference modules named in SURVEY.md section 8(b)):
     Unet3D_with_Conv3D          model/video_diffusion_pytorch/video_diffusion_pytorch_conv3d.py:356
     GaussianDiffusion           diffusion/diffusion_2d_smoke.py:451
     StockSmokeGuidance          inference/inference_2d_smoke.py:30-44 (closed-form, fused into the step kernel)
+Sub-modules mirror the other reference modules of the path:
+    diffusion_2d_jellyfish.GaussianDiffusion    diffusion/diffusion_2d_jellyfish.py:529
+    diffusion_1d_burgers.GaussianDiffusion, get_nablaJ, cosine_beta_J_schedule, ...   diffusion/diffusion_1d_burgers.py
+    burgers_unet.Unet2D                         model/burgers_1d/unet.py:273
+    smoke_rollout.{init_sim_128, init_velocity_, solver}   dataset/apps/evaluate_solver.py
+    burgers.burgers_numeric_solve_free          dataset/apps/generate_burgers.py:207
 The arithmetic lives in libdpc_b200.so (include/dpc_b200.h); there is no CPU or PyTorch fallback.
 """
 from .diffusion_2d_smoke import SMOKE_RESCALER, GaussianDiffusion, StockSmokeGuidance  # noqa: F401
