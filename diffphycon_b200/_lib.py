@@ -62,6 +62,7 @@ _SIGNATURES = {
     "dpc_upsample_nearest2x": ([c_fp, c_fp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_pack_input": ([c_fp, c_fp] + [C.c_int32] * 8 + [c_fp], C.c_int),
     "dpc_temporal_attention": ([c_fp] * 5 + [C.c_int32] * 6 + [c_fp], C.c_int),
+    "dpc_temporal_block_fused": ([c_fp] * 7 + [C.c_int32] * 5 + [C.c_float, c_fp], C.c_int),
     "dpc_spatial_attention": ([c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_spatial_linear_attention": ([c_fp, c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_time_embed": ([c_fp] * 8 + [C.c_int32, C.c_int32, c_fp], C.c_int),
@@ -220,6 +221,18 @@ def temporal_attention(qkv, rope_cos, rope_sin, pos_bias, out, B, F, HW, heads, 
     check(lib().dpc_temporal_attention(ptr(qkv), ptr(rope_cos), ptr(rope_sin), ptr(pos_bias), ptr(out), B, F, HW, heads,
                                        1 if use_rope else 0, 1 if precise else 0, stream_ptr()), "dpc_temporal_attention")
     LaunchCounter.count += 1
+
+
+@_timed("temporal_block_fused")
+def temporal_block_fused(x, w_qkv, w_out, rope_cos, rope_sin, pos_bias, y, B, F, HW, Cn, heads, eps=1e-5) -> bool:
+    """LayerNorm + to_qkv + temporal attention + to_out + residual in one launch; False if the shape is not served (-2)."""
+    rc = lib().dpc_temporal_block_fused(ptr(x), ptr(w_qkv), ptr(w_out), ptr(rope_cos), ptr(rope_sin), ptr(pos_bias), ptr(y),
+                                        B, F, HW, Cn, heads, eps, stream_ptr())
+    if rc == -2:
+        return False
+    check(rc, "dpc_temporal_block_fused")
+    LaunchCounter.count += 1
+    return True
 
 
 @_timed("spatial_attention")

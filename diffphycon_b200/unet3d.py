@@ -286,6 +286,11 @@ class Unet3D_with_Conv3D(nn.Module):
             P[f"{name}.out.w"] = packing.pack_linear(att.to_out.weight.to(dev), tf32=rnd)
             if att.to_out.bias is not None:
                 P[f"{name}.out.b"] = att.to_out.bias.detach().float().to(dev).contiguous()
+            elif kind == "temporal" and rnd:
+                # operands of the fused block kernel (dpc_temporal_block_fused): LayerNorm gain folded into to_qkv
+                wq = att.to_qkv.weight.detach().float().to(dev) * P[f"{name}.gamma"][None, :]
+                P[f"{name}.qkv.wf"] = packing.tf32_round(wq).contiguous()
+                P[f"{name}.out.wf"] = packing.tf32_round(att.to_out.weight.detach().float().to(dev)).contiguous()
 
         pack_attn("init_temporal_attn", self.init_temporal_attn, "temporal")
         for i, lvl in enumerate(self.downs):
@@ -530,6 +535,12 @@ class Unet3D_with_Conv3D(nn.Module):
         def attention(name, xa, c, lvl, kind):
             m = rows(lvl)
             h, w = G[f"hw.{lvl}"]
+            if kind == "temporal" and self.use_tcgen05 and not precise and f"{name}.qkv.wf" in P:
+                y = pool.get(m * c)
+                if _lib.temporal_block_fused(xa, P[f"{name}.qkv.wf"], P[f"{name}.out.wf"], G["rope.cos"], G["rope.sin"],
+                                             G["pos_bias"], y, B, F, h * w, c, heads):
+                    return y
+                pool.put(y)
             xn = pool.get(m * c)
             _lib.layernorm_channels(xa, P[f"{name}.gamma"], xn, m, c)
             qkv = pool.get(m * 3 * hid)

@@ -119,6 +119,16 @@ int dpc_pack_input(const float* x, float* out, int32_t B, int32_t F, int32_t Cto
 int dpc_temporal_attention(const float* qkv, const float* rope_cos, const float* rope_sin, const float* pos_bias,
                            float* out, int32_t B, int32_t F, int32_t HW, int32_t heads, int32_t use_rope,
                            int32_t precise, void* stream);
+/* The whole temporal-attention residual block in one launch (dim 64, 4 heads, F = 32, HW % 4 == 0; returns -2 otherwise and
+ * the caller uses the unfused entry points):  y = x + to_out(Attention(LayerNorm(x)))  — conv3d.py:165-174 (LayerNorm, gain
+ * only), :293-352 (to_qkv, scale, RoPE, relative bias, softmax, to_out without bias), :153-157 (Residual).
+ * x, y: [B, F, HW, 64] channels-last.  w_qkv: [384][64] = to_qkv.weight * LayerNorm gain (gain folded in), TF32-rounded;
+ * w_out: [64][128] = to_out.weight, TF32-rounded.  pos_bias [4][32][32] must be a function of (j - i) only (T5 relative
+ * bias, conv3d.py:74-112): the kernel reads its first row and first column.  Contractions: TF32 tcgen05 MMAs for the two
+ * projections, fp32 for q k^T and P v. */
+int dpc_temporal_block_fused(const float* x, const float* w_qkv, const float* w_out, const float* rope_cos,
+                             const float* rope_sin, const float* pos_bias, float* y, int32_t B, int32_t F, int32_t HW,
+                             int32_t C, int32_t heads, float eps, void* stream);
 /* Softmax attention over the HW tokens of every frame (mid block) — conv3d.py:449-451 with Attention(:293-352),
  * no RoPE, no bias. */
 int dpc_spatial_attention(const float* qkv, float* out, int32_t BF, int32_t HW, int32_t heads, void* stream);

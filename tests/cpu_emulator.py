@@ -142,6 +142,20 @@ def temporal_attention(qkv, rope_cos, rope_sin, pos_bias, out, B, F, HW, heads, 
     out[: o.numel()] = o.reshape(-1)
 
 
+def temporal_block_fused(x, w_qkv, w_out, rope_cos, rope_sin, pos_bias, y, B, F, HW, Cn, heads, eps=1e-5):
+    if F != 32 or Cn != 64 or heads != 4 or HW % 4:
+        return False
+    rows = B * F * HW
+    v = x[: rows * Cn].reshape(rows, Cn)
+    xh = (v - v.mean(1, keepdim=True)) / (v.var(1, unbiased=False, keepdim=True) + eps).sqrt()
+    qkv = (xh.double() @ w_qkv.double().t()).float().reshape(-1)
+    att = torch.empty(rows * heads * HEADS_DIM)
+    temporal_attention(qkv, rope_cos, rope_sin, pos_bias, att, B, F, HW, heads)
+    o = (att.reshape(rows, -1).double() @ w_out.double().t()).float() + v
+    y[: rows * Cn] = o.reshape(-1)
+    return True
+
+
 def spatial_attention(qkv, out, BF, HW, heads):
     hid = heads * HEADS_DIM
     t = qkv[: BF * HW * 3 * hid].reshape(BF, HW, 3 * hid)
@@ -291,7 +305,7 @@ def jelly_write_bd(pred_bd, bd_0, x_next, x_w, cond_steps):
     x_w[:, :, 3:6] = bd
 
 
-EMULATED = ("jelly_x_start", "jelly_step", "jelly_write_bd", "burgers_model_output", "ddpm_posterior_step", "conv", "groupnorm_silu", "layernorm_channels", "pack_input", "temporal_attention", "spatial_attention",
+EMULATED = ("temporal_block_fused", "jelly_x_start", "jelly_step", "jelly_write_bd", "burgers_model_output", "ddpm_posterior_step", "conv", "groupnorm_silu", "layernorm_channels", "pack_input", "temporal_attention", "spatial_attention",
             "spatial_linear_attention", "time_embed", "time_proj", "predict_x_start", "guided_step", "upsample_nearest2x")
 
 

@@ -447,3 +447,35 @@ def test_jellyfish_step_kernels_match_torch_restatement(ddim, guided):
         assert torch.equal(a, b)
     for a, b in zip(outs["cpu"][3:], outs["cuda"][3:]):
         assert (a - b).abs().max().item() <= 1e-6
+
+
+@pytest.mark.parametrize("B,HW", [(1, 4), (2, 64), (3, 148 * 4 + 8)])
+def test_temporal_block_fused_tcgen05(B, HW):
+    """dpc_temporal_block_fused (LayerNorm + to_qkv + RoPE/bias attention + to_out + residual, one launch) against the fp32
+    restatement of conv3d.py:165-174, :293-352 (tests/cpu_emulator.py).  The two projections are TF32 contractions:
+    tolerance 3e-3 of the output scale; the attention itself is fp32."""
+    torch.manual_seed(5)
+    Fr, Cn, heads = 32, 64, 4
+    x = torch.randn(B * Fr * HW * Cn) * 1.5 + 0.3
+    gamma = 1 + 0.1 * torch.randn(Cn)
+    wq = packing.tf32_round((torch.randn(384, Cn) / 8) * gamma[None, :]).contiguous()
+    wo = packing.tf32_round(torch.randn(Cn, 128) / 11).contiguous()
+    ang = torch.arange(Fr, dtype=torch.float32)[:, None] * (10000.0 ** (-torch.arange(0, 32, 2, dtype=torch.float32) / 32))[None, :]
+    ang = ang.repeat_interleave(2, dim=1)
+    cos, sin = ang.cos().contiguous(), ang.sin().contiguous()
+    rel = torch.randn(heads, 63)
+    idx = torch.arange(Fr)[None, :] - torch.arange(Fr)[:, None] + 31
+    bias = rel[:, idx].contiguous()                                      # [heads, i, j], a function of j - i
+    ref = torch.empty_like(x)
+    assert emu.temporal_block_fused(x, wq, wo, cos, sin, bias, ref, B, Fr, HW, Cn, heads)
+    y = torch.empty_like(x, device="cuda")
+    ran = _lib.temporal_block_fused(x.cuda(), wq.cuda(), wo.cuda(), cos.cuda(), sin.cuda(), bias.cuda(), y, B, Fr, HW, Cn, heads)
+    assert ran
+    err = (y.cpu() - ref).abs().max().item() / ref.abs().max().item()
+    assert err <= 3e-3, err
+
+
+def test_temporal_block_fused_declines_other_shapes():
+    z = torch.zeros(16, device="cuda")
+    assert _lib.temporal_block_fused(z, z, z, z, z, z, z, 1, 16, 4, 64, 4) is False
+    assert _lib.temporal_block_fused(z, z, z, z, z, z, z, 1, 32, 4, 128, 4) is False
