@@ -64,6 +64,7 @@ _SIGNATURES = {
     "dpc_temporal_attention": ([c_fp] * 5 + [C.c_int32] * 6 + [c_fp], C.c_int),
     "dpc_temporal_block_fused": ([c_fp] * 7 + [C.c_int32] * 5 + [C.c_float, c_fp], C.c_int),
     "dpc_spatial_attention": ([c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
+    "dpc_spatial_linear_block_fused": ([c_fp] * 7 + [C.c_int32] * 4 + [C.c_float, c_fp], C.c_int),
     "dpc_spatial_linear_attention": ([c_fp, c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_time_embed": ([c_fp] * 8 + [C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_time_proj": ([c_fp] * 4 + [C.c_int32] * 3 + [c_fp], C.c_int),
@@ -239,6 +240,18 @@ def temporal_block_fused(x, w_qkv, w_out, rope_cos, rope_sin, pos_bias, y, B, F,
 def spatial_attention(qkv, out, BF, HW, heads):
     check(lib().dpc_spatial_attention(ptr(qkv), ptr(out), BF, HW, heads, stream_ptr()), "dpc_spatial_attention")
     LaunchCounter.count += 1
+
+
+@_timed("spatial_linear_block_fused")
+def spatial_linear_block_fused(x, w_qkv, w_out, b_out, ctx_ws, mt_ws, y, BF, HW, Cn, heads, eps=1e-5) -> bool:
+    """LayerNorm + to_qkv + linear attention + to_out + residual in three launches; False if the shape is not served."""
+    rc = lib().dpc_spatial_linear_block_fused(ptr(x), ptr(w_qkv), ptr(w_out), ptr(b_out), ptr(ctx_ws), ptr(mt_ws), ptr(y),
+                                              BF, HW, Cn, heads, eps, stream_ptr())
+    if rc == -2:
+        return False
+    check(rc, "dpc_spatial_linear_block_fused")
+    LaunchCounter.count += 3
+    return True
 
 
 @_timed("spatial_linear_attention")

@@ -286,11 +286,14 @@ class Unet3D_with_Conv3D(nn.Module):
             P[f"{name}.out.w"] = packing.pack_linear(att.to_out.weight.to(dev), tf32=rnd)
             if att.to_out.bias is not None:
                 P[f"{name}.out.b"] = att.to_out.bias.detach().float().to(dev).contiguous()
-            elif kind == "temporal" and rnd:
-                # operands of the fused block kernel (dpc_temporal_block_fused): LayerNorm gain folded into to_qkv
-                wq = att.to_qkv.weight.detach().float().to(dev) * P[f"{name}.gamma"][None, :]
+            if kind in ("temporal", "linear") and rnd:
+                # operands of the fused block kernels (dpc_temporal_block_fused, dpc_spatial_linear_block_fused): LayerNorm
+                # gain folded into to_qkv
+                c_in = att.to_qkv.weight.shape[1]
+                wq = att.to_qkv.weight.detach().float().to(dev).reshape(-1, c_in) * P[f"{name}.gamma"][None, :]
                 P[f"{name}.qkv.wf"] = packing.tf32_round(wq).contiguous()
-                P[f"{name}.out.wf"] = packing.tf32_round(att.to_out.weight.detach().float().to(dev)).contiguous()
+                wo = att.to_out.weight.detach().float().to(dev).reshape(c_in, -1)
+                P[f"{name}.out.wf"] = (packing.tf32_round(wo) if kind == "temporal" else wo).contiguous()
 
         pack_attn("init_temporal_attn", self.init_temporal_attn, "temporal")
         for i, lvl in enumerate(self.downs):
@@ -539,6 +542,17 @@ class Unet3D_with_Conv3D(nn.Module):
                 y = pool.get(m * c)
                 if _lib.temporal_block_fused(xa, P[f"{name}.qkv.wf"], P[f"{name}.out.wf"], G["rope.cos"], G["rope.sin"],
                                              G["pos_bias"], y, B, F, h * w, c, heads):
+                    return y
+                pool.put(y)
+            if kind == "linear" and self.use_tcgen05 and not precise and f"{name}.qkv.wf" in P:
+                y = pool.get(m * c)
+                ctx = pool.get(B * F * heads * HEAD_DIM * HEAD_DIM)
+                mt = pool.get(B * F * c * hid)
+                ok = _lib.spatial_linear_block_fused(xa, P[f"{name}.qkv.wf"], P[f"{name}.out.wf"], P.get(f"{name}.out.b"),
+                                                     ctx, mt, y, B * F, h * w, c, heads)
+                pool.put(ctx)
+                pool.put(mt)
+                if ok:
                     return y
                 pool.put(y)
             xn = pool.get(m * c)

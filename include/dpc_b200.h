@@ -137,6 +137,17 @@ int dpc_spatial_attention(const float* qkv, float* out, int32_t BF, int32_t HW, 
 int dpc_spatial_linear_attention(const float* qkv, float* ctx_ws, float* out, int32_t BF, int32_t HW, int32_t heads,
                                  void* stream);
 
+/* The whole spatial-linear-attention residual block (dim 64, 4 heads, HW % 128 == 0; returns -2 otherwise and the caller
+ * uses the unfused entry points):  y = x + to_out(SpatialLinearAttention(LayerNorm(x))) + b  — conv3d.py:165-174 (LayerNorm,
+ * gain only), :232-257 (to_qkv, softmax of q over d, softmax of k over the pixels, context, to_out), :153-157 (Residual).
+ * x, y: [BF, HW, 64] channels-last.  w_qkv: [384][64] = to_qkv.weight * LayerNorm gain, TF32-rounded; w_out: [64][128]
+ * = to_out.weight; b_out: [64] or NULL.  Workspaces: ctx_ws BF*4*32*32 floats (receives the normalised, scaled context),
+ * mt_ws BF*64*128 floats (context folded with to_out).  Three launches; contractions are TF32 tcgen05 MMAs, softmaxes and
+ * the context normalisation fp32. */
+int dpc_spatial_linear_block_fused(const float* x, const float* w_qkv, const float* w_out, const float* b_out,
+                                   float* ctx_ws, float* mt_ws, float* y, int32_t BF, int32_t HW, int32_t C,
+                                   int32_t heads, float eps, void* stream);
+
 /* ---------------------------------------------------------------------------------------------------------
  * Time embedding — conv3d.py:139-151 (SinusoidalPosEmb), :404-409 (time_mlp), :211-214, :222-224 (ResnetBlock.mlp).
  * freqs: [dim/2] table exp(-i*log(10000)/(dim/2-1)).  t_emb out: [B, 4*dim].

@@ -176,6 +176,22 @@ def spatial_linear_attention(qkv, ctx_ws, out, BF, HW, heads):
     out[: o.numel()] = o.reshape(-1)
 
 
+def spatial_linear_block_fused(x, w_qkv, w_out, b_out, ctx_ws, mt_ws, y, BF, HW, Cn, heads, eps=1e-5):
+    if Cn != 64 or heads != 4 or HW % 128:
+        return False
+    rows = BF * HW
+    v = x[: rows * Cn].reshape(rows, Cn)
+    xh = (v - v.mean(1, keepdim=True)) / (v.var(1, unbiased=False, keepdim=True) + eps).sqrt()
+    qkv = (xh.double() @ w_qkv.double().t()).float().reshape(-1)
+    att = torch.empty(rows * heads * HEADS_DIM)
+    spatial_linear_attention(qkv, ctx_ws, att, BF, HW, heads)
+    o = (att.reshape(rows, -1).double() @ w_out.double().t()).float() + v
+    if b_out is not None:
+        o = o + b_out[None, :]
+    y[: rows * Cn] = o.reshape(-1)
+    return True
+
+
 def time_embed(t, freqs, w1, b1, w2, b2, hidden_ws, t_emb, B, dim):
     arg = t.float()[:, None] * freqs[None, :]
     emb = torch.cat((arg.sin(), arg.cos()), dim=-1)

@@ -475,6 +475,42 @@ def test_temporal_block_fused_tcgen05(B, HW):
     assert err <= 3e-3, err
 
 
+@pytest.mark.parametrize("BF,HW,kscale,bias", [(1, 128, 1.0, True), (3, 256, 1.0, False), (2, 4096, 1.0, True),
+                                                (150, 256, 1.0, True), (5, 1024, 8.0, True)])
+def test_spatial_linear_block_fused_tcgen05(BF, HW, kscale, bias):
+    """dpc_spatial_linear_block_fused (LayerNorm + to_qkv + linear attention + to_out + bias + residual) against the fp32
+    restatement of conv3d.py:165-174, :232-257 (tests/cpu_emulator.py).  All four contractions are TF32: tolerance 3e-3 of
+    the output scale.  kscale = 8 spreads the keys over ~e^40 so the online rescaling of the pixel softmax is exercised;
+    BF = 150 gives some persistent CTAs a second frame."""
+    torch.manual_seed(6)
+    Cn, heads = 64, 4
+    x = torch.randn(BF * HW * Cn) * 1.5 + 0.3
+    gamma = 1 + 0.1 * torch.randn(Cn)
+    w = torch.randn(384, Cn) / 8
+    w[128:256] *= kscale
+    wq = packing.tf32_round(w * gamma[None, :]).contiguous()
+    wo = (torch.randn(Cn, 128) / 11 * 30).contiguous()       # the context averages v over the frame: keep the branch visible
+    bo = torch.randn(Cn) if bias else None
+    ref = torch.empty_like(x)
+    ctx = torch.empty(BF * heads * 32 * 32)
+    assert emu.spatial_linear_block_fused(x, wq, wo, bo, ctx, None, ref, BF, HW, Cn, heads)
+    y = torch.empty_like(x, device="cuda")
+    ctx_d = torch.empty(BF * heads * 32 * 32, device="cuda")
+    mt_d = torch.empty(BF * Cn * 128, device="cuda")
+    ran = _lib.spatial_linear_block_fused(x.cuda(), wq.cuda(), wo.cuda(), bo.cuda() if bias else None, ctx_d, mt_d, y, BF, HW,
+                                          Cn, heads)
+    assert ran
+    branch = (ref - x).abs().max().item()
+    err = (y.cpu() - ref).abs().max().item()
+    assert err <= 3e-3 * max(branch, 1.0), (err, branch)
+
+
+def test_spatial_linear_block_fused_declines_other_shapes():
+    z = torch.zeros(16, device="cuda")
+    assert _lib.spatial_linear_block_fused(z, z, z, None, z, z, z, 1, 128, 128, 4) is False
+    assert _lib.spatial_linear_block_fused(z, z, z, None, z, z, z, 1, 64, 64, 4) is False
+
+
 def test_temporal_block_fused_declines_other_shapes():
     z = torch.zeros(16, device="cuda")
     assert _lib.temporal_block_fused(z, z, z, z, z, z, z, 1, 16, 4, 64, 4) is False
