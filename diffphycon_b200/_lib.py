@@ -65,6 +65,7 @@ _SIGNATURES = {
     "dpc_temporal_block_fused": ([c_fp] * 7 + [C.c_int32] * 5 + [C.c_float, c_fp], C.c_int),
     "dpc_spatial_attention": ([c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_spatial_linear_block_fused": ([c_fp] * 7 + [C.c_int32] * 4 + [C.c_float, c_fp], C.c_int),
+    "dpc_stem_conv_tcgen05": ([c_fp] * 4 + [C.c_int32] * 9 + [c_fp], C.c_int),
     "dpc_spatial_linear_attention": ([c_fp, c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_time_embed": ([c_fp] * 8 + [C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_time_proj": ([c_fp] * 4 + [C.c_int32] * 3 + [c_fp], C.c_int),
@@ -240,6 +241,17 @@ def temporal_block_fused(x, w_qkv, w_out, rope_cos, rope_sin, pos_bias, y, B, F,
 def spatial_attention(qkv, out, BF, HW, heads):
     check(lib().dpc_spatial_attention(ptr(qkv), ptr(out), BF, HW, heads, stream_ptr()), "dpc_spatial_attention")
     LaunchCounter.count += 1
+
+
+@_timed("stem_conv_tcgen05")
+def stem_conv(x, w, bias, y, B, F, H, W, Cpad, N, kt, kh, kw) -> bool:
+    """init_conv on the tcgen05 sliding-window kernel; False if the shape is not served (-2)."""
+    rc = lib().dpc_stem_conv_tcgen05(ptr(x), ptr(w), ptr(bias), ptr(y), B, F, H, W, Cpad, N, kt, kh, kw, stream_ptr())
+    if rc == -2:
+        return False
+    check(rc, "dpc_stem_conv_tcgen05")
+    LaunchCounter.count += 1
+    return True
 
 
 @_timed("spatial_linear_block_fused")

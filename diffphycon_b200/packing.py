@@ -45,6 +45,17 @@ def pack_conv3d(weight: torch.Tensor, cin_pad: int | None = None, tf32: bool = T
     return _pad2(mat, npad_of(cout), round_up(mat.shape[1], 32)), kt * kh * kw, cin_eff
 
 
+def pack_stem_conv(weight: torch.Tensor, cin_pad: int, tf32: bool = True):
+    """[Cout,Cin,kt,kh,7] -> [Cout][kt*kh*(cin_pad/4)*32] for csrc/stem_conv_tcgen05.cu: k = (((dt*kh + dh)*P + plane)*8 + dw)*4
+    + c with channel = 4*plane + c; the dw = 7 column and the padded channels are zero."""
+    cout, cin, kt, kh, kw = weight.shape
+    assert kw == 7 and cin_pad % 4 == 0 and cin_pad >= cin
+    w = weight.detach().float().permute(0, 2, 3, 4, 1)                    # [Cout, kt, kh, kw, Cin]
+    w = torch.nn.functional.pad(w, (0, cin_pad - cin, 0, 8 - kw))         # [Cout, kt, kh, 8, cin_pad]
+    w = w.reshape(cout, kt, kh, 8, cin_pad // 4, 4).permute(0, 1, 2, 4, 3, 5).reshape(cout, -1)
+    return (tf32_round(w) if tf32 else w).contiguous()
+
+
 def pack_linear(weight: torch.Tensor, tf32: bool = True):
     """[N,K] (or [N,K,1,1] / [N,K,1,1,1]) -> packed [Npad][Kpad]."""
     n, k = weight.shape[0], weight.shape[1]

@@ -266,6 +266,8 @@ class Unet3D_with_Conv3D(nn.Module):
         P["cpad"] = cpad
         P["init_conv.w"], _, _ = packing.pack_conv3d(self.init_conv.weight.to(dev), cin_pad=cpad, tf32=rnd)
         P["init_conv.b"] = self.init_conv.bias.detach().float().to(dev).contiguous()
+        if rnd and self.init_kernel_size == 7 and self.init_conv.weight.shape[0] in (32, 64, 128):
+            P["init_conv.ws"] = packing.pack_stem_conv(self.init_conv.weight.to(dev), cpad)   # dpc_stem_conv_tcgen05
 
         def pack_resnet(name, blk: ResnetBlock):
             for bn in ("block1", "block2"):
@@ -582,7 +584,10 @@ class Unet3D_with_Conv3D(nn.Module):
         _lib.pack_input(x, xin, B, F, ctot, c0, self.channels, H, W, cpad)
         d0 = self.in_out[0][0]
         h0 = pool.get(m0 * d0)
-        conv(xin, cpad, P["init_conv.w"], P["init_conv.b"], h0, d0, 0, "init")
+        k = self.init_kernel_size
+        if not (self.use_tcgen05 and not precise and "init_conv.ws" in P
+                and _lib.stem_conv(xin, P["init_conv.ws"], P["init_conv.b"], h0, B, F, H, W, cpad, d0, k, k, k)):
+            conv(xin, cpad, P["init_conv.w"], P["init_conv.b"], h0, d0, 0, "init")
         pool.put(xin)
         tap("init_conv", h0, 0, d0)
         h1 = attention("init_temporal_attn", h0, d0, 0, "temporal")

@@ -137,6 +137,13 @@ int dpc_spatial_attention(const float* qkv, float* out, int32_t BF, int32_t HW, 
 int dpc_spatial_linear_attention(const float* qkv, float* ctx_ws, float* out, int32_t BF, int32_t HW, int32_t heads,
                                  void* stream);
 
+/* Stem convolution init_conv — conv3d.py:392, Conv3d(channels, dim, (kt, kh, 7), padding (kt/2, kh/2, 3)) — on tcgen05 with
+ * sliding-window (no-swizzle, overlapping core matrix) operand descriptors over the raw channels-last input.
+ * x: [B,F,H,W,Cpad] (Cpad % 4 == 0, <= 16; padded channels zero), y: [B,F,H,W,N] channels-last, N in {32, 64, 128}.
+ * w: [N][kt*kh*(Cpad/4)*32] with k = (((dt*kh + dh)*(Cpad/4) + plane)*8 + dw)*4 + c, channel = 4*plane + c, the dw = 7 column
+ * zero (diffphycon_b200.packing.pack_stem_conv).  TF32 operands, fp32 accumulate.  Returns -2 for shapes it does not serve. */
+int dpc_stem_conv_tcgen05(const float* x, const float* w, const float* bias, float* y, int32_t B, int32_t F, int32_t H,
+                          int32_t W, int32_t Cpad, int32_t N, int32_t kt, int32_t kh, int32_t kw, void* stream);
 /* The whole spatial-linear-attention residual block (dim 64, 4 heads, HW % 128 == 0; returns -2 otherwise and the caller
  * uses the unfused entry points):  y = x + to_out(SpatialLinearAttention(LayerNorm(x))) + b  — conv3d.py:165-174 (LayerNorm,
  * gain only), :232-257 (to_qkv, softmax of q over d, softmax of k over the pixels, context, to_out), :153-157 (Residual).

@@ -121,6 +121,26 @@ def test_conv_stem_7x7x7_padded_channels():
     assert rel_err(y, ref) <= TOL_TF32
 
 
+@pytest.mark.parametrize("B,Fr,H,W,C,Cout", [(2, 4, 16, 16, 6, 64), (1, 3, 12, 20, 2, 32), (1, 9, 64, 64, 6, 64), (2, 2, 8, 40, 7, 128)])
+def test_stem_conv_tcgen05_sliding_window(B, Fr, H, W, C, Cout):
+    """dpc_stem_conv_tcgen05 (7x7x7 init_conv, conv3d.py:392, on no-swizzle overlapping-core-matrix descriptors) against
+    F.conv3d in fp64; TF32 operand class.  Cases: 2 planes / 1 plane / the metric frame (9 full tiles per frame, frames past
+    both temporal borders) / 7 channels with a ragged padded width."""
+    gen = g(21)
+    cpad = packing.round_up(C, 4)
+    x = torch.randn(B, Fr, C, H, W, generator=gen)
+    w = torch.randn(Cout, C, 7, 7, 7, generator=gen) / (343 * C) ** 0.5
+    bias = torch.randn(Cout, generator=gen)
+    ref = F.conv3d(x.permute(0, 2, 1, 3, 4).double(), w.double(), bias.double(), padding=3).permute(0, 2, 3, 4, 1)
+    xin = torch.empty(B, Fr, H, W, cpad, device=DEV)
+    _lib.pack_input(x.to(DEV).contiguous(), xin, B, Fr, C, 0, C, H, W, cpad)
+    ws = packing.pack_stem_conv(w.to(DEV), cpad)
+    y = torch.full((B, Fr, H, W, Cout), float("nan"), device=DEV)
+    assert _lib.stem_conv(xin, ws, bias.to(DEV), y, B, Fr, H, W, cpad, Cout, 7, 7, 7)
+    torch.cuda.synchronize()
+    assert rel_err(y, ref) <= TOL_TF32
+
+
 def test_pack_input_slice():
     gen = g(3)
     x = torch.randn(2, 3, 6, 8, 12, generator=gen)
