@@ -24,7 +24,6 @@ namespace tc {
 
 constexpr int KCH = 32;            // channels per K block: 32 fp32 = one 128-byte swizzle row
 constexpr int ROW_BYTES = 128;
-constexpr int NA = 2;              // A ring depth
 constexpr int MAXS = 4;
 constexpr int NTHREADS_TC = 384;    // warps 0-3: TMA / MMA / TMEM alloc / idle, warps 4-11: two epilogue groups
 constexpr int APARTS = 3;           // the A box of a block is fetched as APARTS row slabs
@@ -39,11 +38,13 @@ struct Params {
   int S, pitch, R, tiles_f;   // sub-tiles per CTA, smem row pitch, box rows, tiles per frame
   int ndw;                    // 1: one halo box (pitch W+2) serves all nine in-plane taps; 3: one box per dw (pitch W)
   int gemm;                   // 1: 1x1x1 conv / Linear layer (single tap, no halo)
+  int ncol;                   // gemm: column tiles of N outputs accumulated side by side in one pass over A
   int ldy, wrow0;             // output row pitch (floats) and first weight row / output column of this launch
-  int NB;
+  int NA, NB;                 // A ring depth, weight ring depth
   int a_bytes, b_bytes;
   int gn_groups;
   int AB, tmem_cols;
+  int dbg;                    // DPC_TC_DEBUG experiment switches (1: weight boxes fetched once, 2: A boxes fetched once)
 };
 
 template <int N>
@@ -54,6 +55,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;           // 128B swizzle atoms need 1024-byte alignment
+  const int NA = p.NA;
   const uint32_t a_buf = base;
   const uint32_t b_buf = base + NA * p.a_bytes;
   const uint32_t bars = b_buf + p.NB * p.b_bytes;         // 8-byte mbarriers
@@ -68,7 +70,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   const int Cin = p.C1 + p.C2;
   const int nch = Cin / KCH, nch1 = p.C1 / KCH;
   const int nblk = p.gemm ? nch : 3 * nch * p.ndw;       // A boxes per tile
-  const int ntap = p.gemm ? 1 : 9 / p.ndw;               // weight boxes per A box
+  const int ntap = p.gemm ? p.ncol : 9 / p.ndw;          // weight boxes per A box
   const int AB = p.AB;                                   // TMEM accumulator sets (2 = epilogue overlaps the next tile)
   const int ntiles = p.B * p.F * p.tiles_f;
 
@@ -100,7 +102,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     int sa = 0, sb = 0;
     uint32_t pha = 1, phb = 1;                            // producer parity: first pass over a fresh ring does not block
     // state of the A box being fetched (one block ahead of the weight stream)
-    int a_tile = blockIdx.x, a_blk = 0, a_part = 0;
+    int a_tile = blockIdx.x, a_blk = 0, a_part = 0, a_cnt = 0, b_cnt = 0;
     auto issue_a_part = [&]() {
       if (a_tile >= ntiles) return;
       const int tf = a_tile % p.tiles_f;
@@ -120,20 +122,22 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       const int r0 = a_part * rows_part;
       if (a_part == 0) {
         mbar_wait(emptyA + 8 * sa, pha);
-        mbar_expect_tx(fullA + 8 * sa, (uint32_t)(p.R * p.pitch * ROW_BYTES));
+        if ((p.dbg & 2) && a_cnt >= NA) mbar_arrive(fullA + 8 * sa);
+        else mbar_expect_tx(fullA + 8 * sa, (uint32_t)(p.R * p.pitch * ROW_BYTES));
       }
-      if (r0 < p.R) {
+      if (r0 < p.R && !((p.dbg & 2) && a_cnt >= NA)) {
         const CUtensorMap* mp = (r0 + rows_part <= p.R) ? (src1 ? &tmA1 : &tmA2) : (src1 ? &tmA1t : &tmA2t);
         tma_load_5d(a_buf + sa * p.a_bytes + (uint32_t)(r0 * p.pitch * ROW_BYTES), mp, fullA + 8 * sa, c0, dwb - 1,
                     hq - halo + r0, f + dt - 1, b);
       }
       if (++a_part == APARTS) {
         a_part = 0;
+        ++a_cnt;
         if (++sa == NA) { sa = 0; pha ^= 1; }
         if (++a_blk == nblk) { a_blk = 0; a_tile += gridDim.x; }
       }
     };
-    for (int i = 0; i < APARTS; ++i) issue_a_part();      // A box of the very first block
+    for (int i = 0; i < (NA - 1) * APARTS; ++i) issue_a_part();   // the A stream runs NA-1 blocks ahead of the weight stream
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int j = 0; j < nblk; ++j) {
         int dt = 0, ch = j, dwb = 0;
@@ -144,13 +148,17 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           dwb = rem - ch * p.ndw;
         }
         // weight column of tap (dt, dh, dw): ((dt*3 + dh)*3 + dw)*Cin + ch*32; per box either all nine (dh,dw) or the three dh
-        const int k0 = (dt * 9 + dwb) * Cin + ch * KCH;
+        const int k0 = p.gemm ? ch * KCH : (dt * 9 + dwb) * Cin + ch * KCH;
         const int kstep = (p.ndw == 1) ? Cin : 3 * Cin;
         int parts_left = APARTS;
         for (int t = 0; t < ntap; ++t) {
           mbar_wait(emptyB + 8 * sb, phb);
-          mbar_expect_tx(fullB + 8 * sb, (uint32_t)p.b_bytes);
-          tma_load_2d(b_buf + sb * p.b_bytes, &tmW, fullB + 8 * sb, k0 + t * kstep, p.wrow0);
+          if ((p.dbg & 1) && b_cnt >= p.NB) mbar_arrive(fullB + 8 * sb);
+          else {
+            mbar_expect_tx(fullB + 8 * sb, (uint32_t)p.b_bytes);
+            tma_load_2d(b_buf + sb * p.b_bytes, &tmW, fullB + 8 * sb, p.gemm ? k0 : k0 + t * kstep, p.gemm ? p.wrow0 + t * N : p.wrow0);
+          }
+          ++b_cnt;
           if (++sb == p.NB) { sb = 0; phb ^= 1; }
           if ((t + 2 >= p.NB || t + 1 >= ntap - 1) && parts_left > 0) { issue_a_part(); --parts_left; }
         }
@@ -167,9 +175,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     const uint64_t adesc_buf0 = umma_desc(a_buf);
     const uint64_t bdesc_buf0 = umma_desc(b_buf);
     const uint32_t a_step = (uint32_t)(p.a_bytes >> 4), b_step = (uint32_t)(p.b_bytes >> 4);
-    const uint32_t dh_step = (uint32_t)(p.pitch * (ROW_BYTES / 16));
+    const uint32_t dh_step = p.gemm ? 0u : (uint32_t)(p.pitch * (ROW_BYTES / 16));
     const int ndw_in = p.gemm ? 1 : ((p.ndw == 1) ? 3 : 1);   // dw taps served from one A box
-    const int ndh_in = p.gemm ? 1 : 3;
+    const int ndh_in = p.gemm ? p.ncol : 3;                   // gemm: the "dh" loop walks the column tiles (A does not move)
+    const uint32_t col_step = p.gemm ? (uint32_t)(p.S * N) : 0u;
+    const int ncolt = p.gemm ? p.ncol : 1;
     int sa = 0, sb = 0, ab = 0;
     uint32_t pha = 0, phb = 0, phacc = 1;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -180,7 +190,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       const int nsub = (npos >= p.S * 128) ? p.S : (npos + 127) / 128;
       mbar_wait(acc_empty + 8 * ab, phacc);               // epilogue has drained this accumulator set
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tacc = tmem_base + (uint32_t)(ab * p.S * N);
+      const uint32_t tacc = tmem_base + (uint32_t)(ab * p.S * N * ncolt);
       uint32_t first = 0;
       for (int j = 0; j < nblk; ++j) {
         mbar_wait(fullA + 8 * sa, pha);
@@ -189,6 +199,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
 #pragma unroll 1
         for (int dh = 0; dh < ndh_in; ++dh, adesc_dh += dh_step) {
           uint64_t adesc = adesc_dh;
+          const uint32_t tcol = tacc + (uint32_t)dh * col_step;
+          if (p.gemm) first = (j > 0) ? 1u : 0u;
 #pragma unroll 1
           for (int dw = 0; dw < ndw_in; ++dw, adesc += ROW_BYTES / 16) {
             mbar_wait(fullB + 8 * sb, phb);
@@ -200,7 +212,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
                 if (s < nsub) {
 #pragma unroll
                   for (int k = 0; k < KCH / 8; ++k)
-                    umma_tf32(tacc + (uint32_t)(s * N), adesc + (uint64_t)(s * (128 * ROW_BYTES / 16) + 2 * k),
+                    umma_tf32(tcol + (uint32_t)(s * N), adesc + (uint64_t)(s * (128 * ROW_BYTES / 16) + 2 * k),
                               bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
                 }
               }
@@ -241,7 +253,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       for (int g = 0; g < 8; ++g) fs[g] = fq[g] = 0.f;
       mbar_wait(acc_full + 8 * ab, phacc);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.S * N);
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.S * N * (p.gemm ? p.ncol : 1));
       if (p.gemm) {
         // Linear / 1x1x1 epilogue: the tile is store-bound, so rows are staged through a per-warp shared-memory tile
         // (32 rows x 36 floats, conflict-free float4 both ways) and written as 128-byte row segments: a warp store
@@ -249,38 +261,59 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         float* stage = stage_all + (warp - 4) * (32 * 36);
         const size_t frame_base = ((size_t)b * p.F + f) * (size_t)(p.H * p.W);
         const int rsub = lane >> 3, cq = (lane & 7) * 4;
-        for (int s = eg; s < nsub; s += 2) {
-          const int mu_w = mu_tile + s * 128 + q * 32;        // first position of this warp's 32 rows
-#pragma unroll 1
-          for (int c = 0; c < N / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tacc + (uint32_t)(s * N + c * 32), v);
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        // work items = 32-column chunks of every (column tile, sub-tile) accumulator, dealt alternately to the two groups;
+        // the residual of the NEXT item is requested before this item is written (one round trip of latency per item
+        // instead of one per 4-row group)
+        const int cpa = N / 32;
+        const int nitems = nsub * p.ncol * cpa;
+        float4 rnext[8];
+        auto item_geo = [&](int i, int& sN, int& ccol, int& mu_w) {
+          const int acc = i / cpa, c = i - acc * cpa;     // accumulator (ct, s) = ct * S + s
+          const int ct = acc / nsub, ss = acc - ct * nsub;
+          sN = (ct * p.S + ss) * N + c * 32;
+          ccol = p.wrow0 + ct * N + c * 32;
+          mu_w = mu_tile + ss * 128 + q * 32;
+        };
+        auto load_res = [&](int i) {
+          int sN, ccol, mu_w;
+          item_geo(i, sN, ccol, mu_w);
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + c * 32 + j));
-              *reinterpret_cast<float4*>(stage + lane * 36 + j) =
-                  make_float4(__uint_as_float(v[j]) + bv.x, __uint_as_float(v[j + 1]) + bv.y,
-                              __uint_as_float(v[j + 2]) + bv.z, __uint_as_float(v[j + 3]) + bv.w);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int r = it * 4 + rsub;
-              const int mu = mu_w + r;
-              if (mu < p.H * p.W) {
-                float4 ov = *reinterpret_cast<const float4*>(stage + r * 36 + cq);
-                const size_t off = (frame_base + mu) * (size_t)p.ldy + p.wrow0 + c * 32 + cq;
-                if (p.residual) {
-                  const float4 rv = __ldcs(reinterpret_cast<const float4*>(p.residual + off));
-                  ov.x += rv.x; ov.y += rv.y; ov.z += rv.z; ov.w += rv.w;
-                }
-                __stcs(reinterpret_cast<float4*>(p.y + off), ov);
-              }
-            }
-            __syncwarp();
+          for (int it = 0; it < 8; ++it) {
+            const int mu = mu_w + it * 4 + rsub;
+            rnext[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (mu < p.H * p.W) rnext[it] = __ldcs(reinterpret_cast<const float4*>(p.residual + (frame_base + mu) * (size_t)p.ldy + ccol + cq));
           }
+        };
+        if (p.residual && eg < nitems) load_res(eg);
+        for (int i = eg; i < nitems; i += 2) {
+          int sN, ccol, mu_w;
+          item_geo(i, sN, ccol, mu_w);
+          uint32_t v[32];
+          tmem_ld32(tacc + (uint32_t)sN, v);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          const float* bp = p.bias ? p.bias + (ccol - p.wrow0) : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (bp) bv = __ldg(reinterpret_cast<const float4*>(bp + j));
+            *reinterpret_cast<float4*>(stage + lane * 36 + j) =
+                make_float4(__uint_as_float(v[j]) + bv.x, __uint_as_float(v[j + 1]) + bv.y,
+                            __uint_as_float(v[j + 2]) + bv.z, __uint_as_float(v[j + 3]) + bv.w);
+          }
+          __syncwarp();
+          float4 ov[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            ov[it] = *reinterpret_cast<const float4*>(stage + (it * 4 + rsub) * 36 + cq);
+            if (p.residual) { ov[it].x += rnext[it].x; ov[it].y += rnext[it].y; ov[it].z += rnext[it].z; ov[it].w += rnext[it].w; }
+          }
+          if (p.residual && i + 2 < nitems) load_res(i + 2);
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int mu = mu_w + it * 4 + rsub;
+            if (mu < p.H * p.W) __stcs(reinterpret_cast<float4*>(p.y + (frame_base + mu) * (size_t)p.ldy + ccol + cq), ov[it]);
+          }
+          __syncwarp();
         }
       } else
       for (int s = eg; s < nsub; s += 2) {
@@ -450,6 +483,7 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   p.bias = c.bias; p.residual = c.residual; p.y = c.y; p.gn_stats = c.gn_stats; p.gn_groups = c.gn_groups;
   p.B = c.B; p.F = F; p.H = H; p.W = W; p.C1 = c.C1; p.C2 = c.C2; p.Cout = c.Cout;
   p.gemm = gemm ? 1 : 0;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DPC_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   p.ldy = c.Cout;
   p.wrow0 = 0;
   // small frames: padding columns (W+2)/W and the 128-row quantisation of the padded-flat domain waste too much of
@@ -457,10 +491,17 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   p.ndw = (!gemm && W >= 32) ? 1 : 3;
   p.pitch = (p.ndw == 1) ? W + 2 : W;
   const int frame_pos = H * p.pitch;
-  int S = gemm ? 256 / Ntile : 512 / Ntile;            // gemm tiles are store-bound: keep two accumulator sets
+  // gemm: up to 512 accumulator columns = ncol column tiles side by side, so A is read once for (up to) 512 outputs
+  int ncol = 1;
+  if (gemm) { ncol = c.Cout / Ntile; if (ncol * Ntile > 512) ncol = 512 / Ntile; }
+  p.ncol = ncol;
+  int S = gemm ? 256 / (ncol * Ntile) : 512 / Ntile;   // gemm tiles are store-bound: keep two accumulator sets when they fit
+  if (S < 1) S = 1;
   if (S > MAXS) S = MAXS;
   if (S > (frame_pos + 127) / 128) S = (frame_pos + 127) / 128;
   const size_t budget = 227 * 1024 - 2048;
+  const int NA = 2;
+  p.NA = NA;
   p.b_bytes = Ntile * ROW_BYTES;
   for (;; --S) {
     // rows needed: offset inside the first row (< pitch) + S*128 positions (+ two more image rows + 2 positions of halo)
@@ -471,8 +512,8 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   }
   if ((size_t)NA * p.a_bytes + 3 * (size_t)p.b_bytes + 1024 + 256 + 36864 > budget || p.R > 256) return -2;
   p.S = S;
-  p.AB = (2 * S * Ntile <= 512) ? 2 : 1;
-  { int need = p.AB * S * Ntile; p.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512; }
+  p.AB = (2 * S * ncol * Ntile <= 512) ? 2 : 1;
+  { int need = p.AB * S * ncol * Ntile; p.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512; }
   p.tiles_f = (frame_pos + S * 128 - 1) / (S * 128);
   const size_t stage_bytes = gemm ? (size_t)8 * 32 * 36 * sizeof(float) : 0;
   int NB = (int)((budget - 1024 - 256 - stage_bytes - (size_t)NA * p.a_bytes) / p.b_bytes);
@@ -501,7 +542,8 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   rc = make_w_map(&wm, c.w, c.Kpad, c.Npad, Ntile);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
-  for (int n0 = 0; n0 < c.Cout; n0 += Ntile) {
+  for (int n0 = 0; n0 < c.Cout; n0 += ncol * Ntile) {
+    if (gemm && c.Cout - n0 < ncol * Ntile) p.ncol = (c.Cout - n0) / Ntile;
     p.wrow0 = n0;
     p.bias = c.bias ? c.bias + n0 : nullptr;
     if (Ntile == 64) rc = launch<64>(a1, a2, a1t, a2t, wm, p, smem, st);
