@@ -47,7 +47,49 @@ struct Params {
   int dbg;                    // DPC_TC_DEBUG experiment switches (1: weight boxes fetched once, 2: A boxes fetched once)
 };
 
-template <int N>
+// cta_group::2 helpers (PAIR mode): the two CTAs of a cluster run one M = 256 MMA per instruction.  Each CTA keeps its own A
+// tile (128 rows) and HALF of the weight box (N/2 rows) in its shared memory, so the weight operand is read once per pair
+// instead of once per CTA (the tensor pipe is fed from shared memory at < 100 B/clk; measured).  The leader
+// (cluster rank 0) issues the MMAs; every TMA of either CTA completes on the leader's "full" barriers; tcgen05.commit
+// multicasts the "empty" / "accumulator full" arrivals to both CTAs.
+__device__ __forceinline__ uint32_t leader_addr(uint32_t local) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local), "r"(0));
+  return r;
+}
+__device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_leader, int c0, int c1, int c2,
+                                                 int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_leader), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_leader, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_leader), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int N, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS_TC, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmA1t, const __grid_constant__ CUtensorMap tmA2t,
@@ -73,22 +115,42 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   const int ntap = p.gemm ? p.ncol : 9 / p.ndw;          // weight boxes per A box
   const int AB = p.AB;                                   // TMEM accumulator sets (2 = epilogue overlaps the next tile)
   const int ntiles = p.B * p.F * p.tiles_f;
+  // PAIR: the two CTAs of a cluster take the same spatial tile tf of two consecutive frames (same operand offsets in both
+  // shared memories, which one shared A descriptor requires); iterations then count tile pairs.
+  uint32_t cta_rank = 0;
+  if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+  const bool leader = cta_rank == 0;
+  const int it_begin = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int it_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int it_end = PAIR ? ntiles / 2 : ntiles;
+  auto tile_of = [&](int it) {
+    if (!PAIR) return it;
+    const int bfp = it / p.tiles_f;
+    return (2 * bfp + (int)cta_rank) * p.tiles_f + (it - bfp * p.tiles_f);
+  };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < NA; ++i) { mbar_init(fullA + 8 * i, 1); mbar_init(emptyA + 8 * i, 1); }
     for (int i = 0; i < p.NB; ++i) { mbar_init(fullB + 8 * i, 1); mbar_init(emptyB + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, PAIR ? 16 : 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (PAIR) cluster_sync_all();                          // both CTAs' barriers are initialised before any remote signal
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
@@ -102,9 +164,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     int sa = 0, sb = 0;
     uint32_t pha = 1, phb = 1;                            // producer parity: first pass over a fresh ring does not block
     // state of the A box being fetched (one block ahead of the weight stream)
-    int a_tile = blockIdx.x, a_blk = 0, a_part = 0, a_cnt = 0, b_cnt = 0;
+    int a_it = it_begin, a_blk = 0, a_part = 0, a_cnt = 0, b_cnt = 0;
+    const uint32_t fullA_l = PAIR ? leader_addr(fullA) : fullA, fullB_l = PAIR ? leader_addr(fullB) : fullB;
+    const int brow = PAIR ? (int)cta_rank * (N / 2) : 0;   // this CTA's half of the weight rows
     auto issue_a_part = [&]() {
-      if (a_tile >= ntiles) return;
+      if (a_it >= it_end) return;
+      const int a_tile = tile_of(a_it);
       const int tf = a_tile % p.tiles_f;
       const int f = (a_tile / p.tiles_f) % p.F;
       const int b = a_tile / (p.tiles_f * p.F);
@@ -122,23 +187,25 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       const int r0 = a_part * rows_part;
       if (a_part == 0) {
         mbar_wait(emptyA + 8 * sa, pha);
-        if ((p.dbg & 2) && a_cnt >= NA) mbar_arrive(fullA + 8 * sa);
+        if (PAIR) { if (leader) mbar_expect_tx(fullA + 8 * sa, (uint32_t)(2 * p.R * p.pitch * ROW_BYTES)); }
+        else if ((p.dbg & 2) && a_cnt >= NA) mbar_arrive(fullA + 8 * sa);
         else mbar_expect_tx(fullA + 8 * sa, (uint32_t)(p.R * p.pitch * ROW_BYTES));
       }
-      if (r0 < p.R && !((p.dbg & 2) && a_cnt >= NA)) {
+      if (r0 < p.R && !(!PAIR && (p.dbg & 2) && a_cnt >= NA)) {
         const CUtensorMap* mp = (r0 + rows_part <= p.R) ? (src1 ? &tmA1 : &tmA2) : (src1 ? &tmA1t : &tmA2t);
-        tma_load_5d(a_buf + sa * p.a_bytes + (uint32_t)(r0 * p.pitch * ROW_BYTES), mp, fullA + 8 * sa, c0, dwb - 1,
-                    hq - halo + r0, f + dt - 1, b);
+        const uint32_t dst = a_buf + sa * p.a_bytes + (uint32_t)(r0 * p.pitch * ROW_BYTES);
+        if (PAIR) tma_load_5d_pair(dst, mp, fullA_l + 8 * sa, c0, dwb - 1, hq - halo + r0, f + dt - 1, b);
+        else tma_load_5d(dst, mp, fullA + 8 * sa, c0, dwb - 1, hq - halo + r0, f + dt - 1, b);
       }
       if (++a_part == APARTS) {
         a_part = 0;
         ++a_cnt;
         if (++sa == NA) { sa = 0; pha ^= 1; }
-        if (++a_blk == nblk) { a_blk = 0; a_tile += gridDim.x; }
+        if (++a_blk == nblk) { a_blk = 0; a_it += it_step; }
       }
     };
     for (int i = 0; i < (NA - 1) * APARTS; ++i) issue_a_part();   // the A stream runs NA-1 blocks ahead of the weight stream
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int it = it_begin; it < it_end; it += it_step) {
       for (int j = 0; j < nblk; ++j) {
         int dt = 0, ch = j, dwb = 0;
         if (!p.gemm) {
@@ -153,7 +220,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         int parts_left = APARTS;
         for (int t = 0; t < ntap; ++t) {
           mbar_wait(emptyB + 8 * sb, phb);
-          if ((p.dbg & 1) && b_cnt >= p.NB) mbar_arrive(fullB + 8 * sb);
+          if (PAIR) {
+            if (leader) mbar_expect_tx(fullB + 8 * sb, (uint32_t)(2 * p.b_bytes));
+            tma_load_2d_pair(b_buf + sb * p.b_bytes, &tmW, fullB_l + 8 * sb, k0 + t * kstep, p.wrow0 + brow);
+          } else if ((p.dbg & 1) && b_cnt >= p.NB) mbar_arrive(fullB + 8 * sb);
           else {
             mbar_expect_tx(fullB + 8 * sb, (uint32_t)p.b_bytes);
             tma_load_2d(b_buf + sb * p.b_bytes, &tmW, fullB + 8 * sb, p.gemm ? k0 : k0 + t * kstep, p.gemm ? p.wrow0 + t * N : p.wrow0);
@@ -165,13 +235,14 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         while (parts_left > 0) { issue_a_part(); --parts_left; }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 && leader) {
     // ------------------------------------------- MMA issuer ---------------------------------------------
     // The whole warp walks the pipeline (warp-uniform control flow, no divisions in the loop); one elected lane
     // issues.  Descriptors are advanced by integer adds on the 16-byte-unit start-address field: +2 per K=8 step
     // (32 B), +1024 per 128-row sub-tile, +8 per dw, +8*pitch per dh.
     // instruction descriptor: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), K-major both, N>>3 at bit 17, M>>4 at bit 24
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) |
+                           ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
     const uint64_t adesc_buf0 = umma_desc(a_buf);
     const uint64_t bdesc_buf0 = umma_desc(b_buf);
     const uint32_t a_step = (uint32_t)(p.a_bytes >> 4), b_step = (uint32_t)(p.b_bytes >> 4);
@@ -182,7 +253,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     const int ncolt = p.gemm ? p.ncol : 1;
     int sa = 0, sb = 0, ab = 0;
     uint32_t pha = 0, phb = 0, phacc = 1;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int it = it_begin; it < it_end; it += it_step) {
+      const int tile = tile_of(it);
       const int tf = tile % p.tiles_f;
       const int mu_tile = tf * p.S * 128;
       const int mu0 = mu_tile - (mu_tile / p.pitch) * p.pitch;
@@ -211,23 +283,29 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
               for (int s = 0; s < MAXS; ++s) {
                 if (s < nsub) {
 #pragma unroll
-                  for (int k = 0; k < KCH / 8; ++k)
-                    umma_tf32(tcol + (uint32_t)(s * N), adesc + (uint64_t)(s * (128 * ROW_BYTES / 16) + 2 * k),
-                              bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
+                  for (int k = 0; k < KCH / 8; ++k) {
+                    if (PAIR)
+                      umma_tf32_pair(tcol + (uint32_t)(s * N), adesc + (uint64_t)(s * (128 * ROW_BYTES / 16) + 2 * k),
+                                     bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
+                    else
+                      umma_tf32(tcol + (uint32_t)(s * N), adesc + (uint64_t)(s * (128 * ROW_BYTES / 16) + 2 * k),
+                                bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
+                  }
                 }
               }
-              umma_commit(emptyB + 8 * sb);               // weight slot is free once these MMAs retire
+              if (PAIR) umma_commit_pair(emptyB + 8 * sb);
+              else umma_commit(emptyB + 8 * sb);          // weight slot is free once these MMAs retire
             }
             __syncwarp();
             first = 1;
             if (++sb == p.NB) { sb = 0; phb ^= 1; }
           }
         }
-        if (elect_one()) umma_commit(emptyA + 8 * sa);
+        if (elect_one()) { if (PAIR) umma_commit_pair(emptyA + 8 * sa); else umma_commit(emptyA + 8 * sa); }
         __syncwarp();
         if (++sa == NA) { sa = 0; pha ^= 1; }
       }
-      if (elect_one()) umma_commit(acc_full + 8 * ab);   // accumulators of this tile are complete
+      if (elect_one()) { if (PAIR) umma_commit_pair(acc_full + 8 * ab); else umma_commit(acc_full + 8 * ab); }   // tile complete
       __syncwarp();
       if (++ab == AB) { ab = 0; phacc ^= 1; }
     }
@@ -241,7 +319,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     constexpr int GW = 32 / GPC;                          // columns of one group inside a chunk
     int ab = 0;
     uint32_t phacc = 0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const uint32_t acc_empty_l = PAIR ? leader_addr(acc_empty) : acc_empty;
+    for (int it = it_begin; it < it_end; it += it_step) {
+      const int tile = tile_of(it);
       const int tf = tile % p.tiles_f;
       const int f = (tile / p.tiles_f) % p.F;
       const int b = tile / (p.tiles_f * p.F);
@@ -368,7 +448,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       // accumulator set drained: hand it back to the MMA warp before the (slower) statistics reduction
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty + 8 * ab) : "memory");
+      if (lane == 0) {
+        if (PAIR) mbar_arrive_cluster(acc_empty_l + 8 * ab);
+        else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(acc_empty + 8 * ab) : "memory");
+      }
       if (++ab == AB) { ab = 0; phacc ^= 1; }
       if (do_stats) {
         // recursive-halving warp reduction of 16 doubles (8 sums, 8 sums of squares): 16 exchanges instead of 80
@@ -402,8 +485,10 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (PAIR) cluster_sync_all();                          // the peer may still signal this CTA's barriers / read its operands
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
 }
 
@@ -434,12 +519,13 @@ static int make_w_map(CUtensorMap* m, const float* w, int Kpad, int Npad, int N)
   return 0;
 }
 
-template <int N>
+template <int N, bool PAIR>
 static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& a1t, const CUtensorMap& a2t,
                   const CUtensorMap& wm, const Params& p, size_t smem, cudaStream_t st) {
   static size_t configured = 0;
   if (smem > configured) {
-    DPC_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DPC_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<N, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (PAIR) DPC_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<N, PAIR>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
     configured = smem;
   }
   const size_t ntiles = (size_t)p.B * p.F * p.tiles_f;
@@ -449,8 +535,36 @@ static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMa
     DPC_CUDA(cudaGetDevice(&dev));
     DPC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
   }
-  const unsigned grid = (unsigned)(ntiles < (size_t)num_sms ? ntiles : (size_t)num_sms);   // persistent: one CTA per SM
-  conv3d_tc_kernel<N><<<grid, NTHREADS_TC, smem, st>>>(a1, a2, a1t, a2t, wm, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(NTHREADS_TC);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (PAIR) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    // persistent CTA pairs: as many clusters as can be co-resident (an SM pair of one TPC each)
+    static int max_clusters = 0;
+    static size_t clusters_smem = 0;
+    if (!max_clusters || smem > clusters_smem) {
+      cfg.gridDim = dim3((unsigned)(num_sms & ~1));
+      int n = 0;
+      DPC_CUDA(cudaOccupancyMaxActiveClusters(&n, conv3d_tc_kernel<N, PAIR>, &cfg));
+      if (n < 1) return set_err(-1, "no co-resident CTA pair for conv3d_tc_kernel", __FILE__, __LINE__);
+      max_clusters = n;
+      clusters_smem = smem;
+    }
+    size_t pairs = ntiles / 2;
+    if (pairs > (size_t)max_clusters) pairs = (size_t)max_clusters;
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+  } else {
+    cfg.gridDim = dim3((unsigned)(ntiles < (size_t)num_sms ? ntiles : (size_t)num_sms));   // persistent: one CTA per SM
+  }
+  DPC_CUDA(cudaLaunchKernelEx(&cfg, conv3d_tc_kernel<N, PAIR>, a1, a2, a1t, a2t, wm, p));
   DPC_LAUNCH_CHECK();
   return 0;
 }
@@ -478,6 +592,9 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   if (c.gn_stats && c.gn_groups != 8) return -2;   // the epilogue is specialised for GroupNorm(8), the reference default
   DPC_CHECK_ARG(c.x1 && c.w && c.y && (c.C2 == 0 || c.x2));
   const bool gemm = !conv_ok;
+  // cta_group::2 pairs (two consecutive frames per cluster) for the 3x3x3 convolutions; DPC_TC_PAIR=0 disables
+  const char* pair_env = getenv("DPC_TC_PAIR");          // read per call: the tests run every shape both ways
+  const bool pair = !gemm && !(pair_env && atoi(pair_env) == 0) && ((int64_t)c.B * F) % 2 == 0;
   const int Ntile = gemm ? (c.Cout == 64 ? 64 : (c.Cout == 256 ? 256 : 128)) : c.Cout;
   Params p;
   p.bias = c.bias; p.residual = c.residual; p.y = c.y; p.gn_stats = c.gn_stats; p.gn_groups = c.gn_groups;
@@ -500,22 +617,25 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   if (S > MAXS) S = MAXS;
   if (S > (frame_pos + 127) / 128) S = (frame_pos + 127) / 128;
   const size_t budget = 227 * 1024 - 2048;
-  const int NA = 2;
-  p.NA = NA;
-  p.b_bytes = Ntile * ROW_BYTES;
+  const size_t stage_bytes = gemm ? (size_t)8 * 32 * 36 * sizeof(float) : 0;
+  int NA = 2;
+  p.b_bytes = (pair ? Ntile / 2 : Ntile) * ROW_BYTES;    // a pair splits every weight box between its two CTAs
   for (;; --S) {
     // rows needed: offset inside the first row (< pitch) + S*128 positions (+ two more image rows + 2 positions of halo)
     const int span = p.pitch - 1 + S * 128 + (gemm ? 0 : 2 * p.pitch + 2);
     p.R = (span + p.pitch - 1) / p.pitch;
     p.a_bytes = ((p.R * p.pitch * ROW_BYTES + 1023) / 1024) * 1024;
-    if ((size_t)NA * p.a_bytes + 3 * (size_t)p.b_bytes + 1024 + 256 + 36864 <= budget || S == 1) break;
+    if ((size_t)NA * p.a_bytes + 3 * (size_t)p.b_bytes + 1024 + 256 + stage_bytes <= budget || S == 1) break;
   }
-  if ((size_t)NA * p.a_bytes + 3 * (size_t)p.b_bytes + 1024 + 256 + 36864 > budget || p.R > 256) return -2;
+  if ((size_t)NA * p.a_bytes + 3 * (size_t)p.b_bytes + 1024 + 256 + stage_bytes > budget || p.R > 256) return -2;
+  // per-dw boxes serve only three taps each: a third slot keeps two of them in flight behind the one being multiplied
+  if (!gemm && p.ndw == 3 && (size_t)3 * p.a_bytes + 3 * (size_t)p.b_bytes + 1024 + 256 <= budget) NA = 3;
+  { static int na_dbg = -1; if (na_dbg < 0) { const char* e = getenv("DPC_TC_NA"); na_dbg = e ? atoi(e) : 0; } if (na_dbg) NA = na_dbg; }
+  p.NA = NA;
   p.S = S;
   p.AB = (2 * S * ncol * Ntile <= 512) ? 2 : 1;
   { int need = p.AB * S * ncol * Ntile; p.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512; }
   p.tiles_f = (frame_pos + S * 128 - 1) / (S * 128);
-  const size_t stage_bytes = gemm ? (size_t)8 * 32 * 36 * sizeof(float) : 0;
   int NB = (int)((budget - 1024 - 256 - stage_bytes - (size_t)NA * p.a_bytes) / p.b_bytes);
   if (NB > 9) NB = 9;
   if (NB < 2) return -2;
@@ -539,16 +659,20 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
     a2 = a1;
     a2t = a1t;
   }
-  rc = make_w_map(&wm, c.w, c.Kpad, c.Npad, Ntile);
+  rc = make_w_map(&wm, c.w, c.Kpad, c.Npad, pair ? Ntile / 2 : Ntile);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   for (int n0 = 0; n0 < c.Cout; n0 += ncol * Ntile) {
     if (gemm && c.Cout - n0 < ncol * Ntile) p.ncol = (c.Cout - n0) / Ntile;
     p.wrow0 = n0;
     p.bias = c.bias ? c.bias + n0 : nullptr;
-    if (Ntile == 64) rc = launch<64>(a1, a2, a1t, a2t, wm, p, smem, st);
-    else if (Ntile == 128) rc = launch<128>(a1, a2, a1t, a2t, wm, p, smem, st);
-    else rc = launch<256>(a1, a2, a1t, a2t, wm, p, smem, st);
+    if (pair) {
+      if (Ntile == 64) rc = launch<64, true>(a1, a2, a1t, a2t, wm, p, smem, st);
+      else if (Ntile == 128) rc = launch<128, true>(a1, a2, a1t, a2t, wm, p, smem, st);
+      else rc = launch<256, true>(a1, a2, a1t, a2t, wm, p, smem, st);
+    } else if (Ntile == 64) rc = launch<64, false>(a1, a2, a1t, a2t, wm, p, smem, st);
+    else if (Ntile == 128) rc = launch<128, false>(a1, a2, a1t, a2t, wm, p, smem, st);
+    else rc = launch<256, false>(a1, a2, a1t, a2t, wm, p, smem, st);
     if (rc) return rc;
   }
   return 0;

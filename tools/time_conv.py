@@ -22,6 +22,10 @@ def run(B, Fr, S, cin, cout, tc=True, reps=5):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     fl = 2.0 * B * Fr * S * S * cin * cout * 27
-    print(f"DPC_TC_DEBUG={os.environ.get('DPC_TC_DEBUG','0')} B={B} S={S} {cin}->{cout}: {ms:.3f} ms {fl/ms/1e9:.0f} TFLOP/s", flush=True)
+    print(f"PAIR={os.environ.get('DPC_TC_PAIR','1')} DBG={os.environ.get('DPC_TC_DEBUG','0')} B={B} S={S} {cin}->{cout}: {ms:.3f} ms {fl/ms/1e9:.0f} TFLOP/s", flush=True)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-run(B, 32, 64, 64, 64); run(B, 32, 32, 128, 128); run(B, 32, 16, 256, 256)
+shapes = [(64, 64, 64), (32, 128, 128), (16, 256, 256)]
+if len(sys.argv) > 2 and sys.argv[2] == "all":
+    shapes += [(64, 128, 64), (16, 512, 128), (16, 128, 128), (32, 256, 64), (32, 64, 64), (32, 64, 128), (16, 128, 256)]
+for S_, ci, co in shapes:
+    run(B, 32, S_, ci, co)
