@@ -594,7 +594,9 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   const bool gemm = !conv_ok;
   // cta_group::2 pairs (two consecutive frames per cluster) for the 3x3x3 convolutions; DPC_TC_PAIR=0 disables
   const char* pair_env = getenv("DPC_TC_PAIR");          // read per call: the tests run every shape both ways
-  const bool pair = !gemm && !(pair_env && atoi(pair_env) == 0) && ((int64_t)c.B * F) % 2 == 0;
+  // (W >= 32 only: with per-dw boxes the pair's lock-step exposes the A latency and measures slower than single CTAs)
+  const bool pair = !gemm && !(pair_env && atoi(pair_env) == 0) && ((int64_t)c.B * F) % 2 == 0 &&
+                    (W >= 32 || (pair_env && atoi(pair_env) == 2));
   const int Ntile = gemm ? (c.Cout == 64 ? 64 : (c.Cout == 256 ? 256 : 128)) : c.Cout;
   Params p;
   p.bias = c.bias; p.residual = c.residual; p.y = c.y; p.gn_stats = c.gn_stats; p.gn_groups = c.gn_groups;
