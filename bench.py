@@ -277,8 +277,16 @@ def main():
         kms = e0.elapsed_time(e1) / reps
         flops = 2.0 * Bc * FRAMES * SIZE * SIZE * 64 * 64 * 27
         ach = flops / (kms / 1e3) / 1e12
+        traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
+        try:
+            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_dominant_kernel_traffic.json")))
+            if used_tc and tj.get("kernel_batch") == Bc:
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        except (OSError, ValueError, KeyError):
+            traffic = None
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["tensor_burst"], "unit": "TFLOP/s",
-                "frac": ach / pk["tensor_burst"], "traffic": None,
+                "frac": ach / pk["tensor_burst"], "traffic": traffic,
+                "traffic_note": "bytes per launch (ncu, profiles/r1_ncu_full_v7.txt); algorithmic = %d" % (2 * Bc * FRAMES * SIZE * SIZE * 64 * 4),
                 "kernel": "conv3d_tcgen05 3x3x3 64->64" if used_tc else "conv_igemm (mma.sync) 3x3x3 64->64",
                 "kernel_ms": kms, "kernel_batch": Bc, "peak_source": pk["source"] + " bf16 burst (kernel timed alone); TF32 nominal peak is half of bf16",
                 "step_tensor_tflops": FLOPS_PER_SAMPLE_STEP * B / (ms_per_step / 1e3) / 1e12,

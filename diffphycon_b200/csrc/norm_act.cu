@@ -57,6 +57,36 @@ groupnorm_silu_kernel(const float* __restrict__ y, const double* __restrict__ st
     float4* o4 = reinterpret_cast<float4*>(out + base);
     const size_t n4 = n >> 2;
     const int c4n = C >> 2;
+    if ((256 % c4n) == 0) {
+      // fast path (C = 16..1024, power of two): a thread always meets the same four channels, so their folded affine
+      //   t = v * (rstd*gamma) + (beta - mean*rstd*gamma),  t = t * (scale+1) + shift
+      // lives in registers; exp and the reciprocal go to the SFU (|error| ~1e-6 relative, the entry point's tolerance
+      // class is 2e-5).  The kernel was issue-bound (64-bit modulo, six shared loads and an IEEE division per float4).
+      const int c = (int)(threadIdx.x % c4n) * 4;
+      float a1[4], b1[4], sc[4], sh[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        a1[k] = s_mul[c + k] * s_g[c + k];
+        b1[k] = fmaf(-s_sub[c + k], a1[k], s_b[c + k]);
+        sc[k] = s_sc[c + k];
+        sh[k] = s_sh[c + k];
+      }
+#pragma unroll 4
+      for (size_t i = threadIdx.x; i < n4; i += 256) {
+        const float4 v = __ldcs(y4 + i);
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r4) r = __ldcs(r4 + i);
+        float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          float t = fmaf(vv[k], a1[k], b1[k]);
+          if (has_ss) t = fmaf(t, sc[k], sh[k]);
+          vv[k] = __fdividef(t, 1.0f + __expf(-t));
+        }
+        __stcs(o4 + i, make_float4(vv[0] + r.x, vv[1] + r.y, vv[2] + r.z, vv[3] + r.w));
+      }
+      return;
+    }
     for (size_t i = threadIdx.x; i < n4; i += blockDim.x) {
       const int c = (int)(i % c4n) * 4;
       float4 v = __ldcs(y4 + i);
