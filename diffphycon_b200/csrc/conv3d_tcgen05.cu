@@ -44,6 +44,10 @@ struct Params {
   int a_bytes, b_bytes;
   int gn_groups;
   int AB, tmem_cols;
+  int mode;                   // 0: 3x3x3 / Linear; 1: 1x4x4 stride-2 down-conv (four parity boxes fetched with TMA traversal
+                              // stride 2, 2x2 taps each); 2: one parity class of the 1x4x4 stride-2 ConvTranspose (2x2 taps)
+  int cls_h, cls_w;           // mode 2: output parity class
+  int Hout, Wout, o_mul;      // output frame and position scale: out(h, w) -> (h*o_mul + cls_h, w*o_mul + cls_w)
   int dbg;                    // DPC_TC_DEBUG experiment switches (1: weight boxes fetched once, 2: A boxes fetched once)
 };
 
@@ -111,8 +115,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Cin = p.C1 + p.C2;
   const int nch = Cin / KCH, nch1 = p.C1 / KCH;
-  const int nblk = p.gemm ? nch : 3 * nch * p.ndw;       // A boxes per tile
-  const int ntap = p.gemm ? p.ncol : 9 / p.ndw;          // weight boxes per A box
+  const int nblk = p.mode == 1 ? 4 * nch : p.mode == 2 ? nch : p.gemm ? nch : 3 * nch * p.ndw;   // A boxes per tile
+  const int ntap = p.mode ? 4 : p.gemm ? p.ncol : 9 / p.ndw;                                       // weight boxes per A box
   const int AB = p.AB;                                   // TMEM accumulator sets (2 = epilogue overlaps the next tile)
   const int ntiles = p.B * p.F * p.tiles_f;
   // PAIR: the two CTAs of a cluster take the same spatial tile tf of two consecutive frames (same operand offsets in both
@@ -175,7 +179,16 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       const int b = a_tile / (p.tiles_f * p.F);
       const int hq = (tf * p.S * 128) / p.pitch;
       int dt = 1, ch = a_blk, dwb = 1, halo = 0;             // gemm: centre tap only, no halo
-      if (!p.gemm) {
+      int w0 = 0, h0 = 0;
+      if (p.mode == 1) {                                     // parity box (ph, pw): input rows 2h + ph - 1 + 2*{0,1}, same in w
+        const int par = a_blk / nch;
+        ch = a_blk - par * nch;
+        h0 = 2 * hq + ((par >> 1) ? -1 : 0);
+        w0 = (par & 1) ? -1 : 0;
+      } else if (p.mode == 2) {                              // class (cls_h, cls_w): input rows h - (1 - cls_h) + {0,1}
+        h0 = hq - (1 - p.cls_h);
+        w0 = -(1 - p.cls_w);
+      } else if (!p.gemm) {
         dt = a_blk / (nch * p.ndw);
         const int rem = a_blk - dt * nch * p.ndw;
         ch = rem / p.ndw;
@@ -194,7 +207,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       if (r0 < p.R && !(!PAIR && (p.dbg & 2) && a_cnt >= NA)) {
         const CUtensorMap* mp = (r0 + rows_part <= p.R) ? (src1 ? &tmA1 : &tmA2) : (src1 ? &tmA1t : &tmA2t);
         const uint32_t dst = a_buf + sa * p.a_bytes + (uint32_t)(r0 * p.pitch * ROW_BYTES);
-        if (PAIR) tma_load_5d_pair(dst, mp, fullA_l + 8 * sa, c0, dwb - 1, hq - halo + r0, f + dt - 1, b);
+        if (p.mode) tma_load_5d(dst, mp, fullA + 8 * sa, c0, w0, h0 + (p.mode == 1 ? 2 * r0 : r0), f, b);
+        else if (PAIR) tma_load_5d_pair(dst, mp, fullA_l + 8 * sa, c0, dwb - 1, hq - halo + r0, f + dt - 1, b);
         else tma_load_5d(dst, mp, fullA + 8 * sa, c0, dwb - 1, hq - halo + r0, f + dt - 1, b);
       }
       if (++a_part == APARTS) {
@@ -208,7 +222,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     for (int it = it_begin; it < it_end; it += it_step) {
       for (int j = 0; j < nblk; ++j) {
         int dt = 0, ch = j, dwb = 0;
-        if (!p.gemm) {
+        int par = 0;
+        if (p.mode) {
+          par = j / nch;
+          ch = j - par * nch;
+        } else if (!p.gemm) {
           dt = j / (nch * p.ndw);
           const int rem = j - dt * nch * p.ndw;
           ch = rem / p.ndw;
@@ -225,8 +243,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             tma_load_2d_pair(b_buf + sb * p.b_bytes, &tmW, fullB_l + 8 * sb, k0 + t * kstep, p.wrow0 + brow);
           } else if ((p.dbg & 1) && b_cnt >= p.NB) mbar_arrive(fullB + 8 * sb);
           else {
+            int kk = p.gemm ? k0 : k0 + t * kstep;
+            if (p.mode == 1)        // tap (sa, sb) of parity (ph, pw) is kernel element (2 sa + 1 - ph, 2 sb + 1 - pw)
+              kk = ((2 * (t >> 1) + 1 - (par >> 1)) * 4 + 2 * (t & 1) + 1 - (par & 1)) * Cin + ch * KCH;
+            else if (p.mode == 2)
+              kk = t * Cin + ch * KCH;
             mbar_expect_tx(fullB + 8 * sb, (uint32_t)p.b_bytes);
-            tma_load_2d(b_buf + sb * p.b_bytes, &tmW, fullB + 8 * sb, p.gemm ? k0 : k0 + t * kstep, p.gemm ? p.wrow0 + t * N : p.wrow0);
+            tma_load_2d(b_buf + sb * p.b_bytes, &tmW, fullB + 8 * sb, kk, p.gemm ? p.wrow0 + t * N : p.wrow0);
           }
           ++b_cnt;
           if (++sb == p.NB) { sb = 0; phb ^= 1; }
@@ -247,8 +270,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     const uint64_t bdesc_buf0 = umma_desc(b_buf);
     const uint32_t a_step = (uint32_t)(p.a_bytes >> 4), b_step = (uint32_t)(p.b_bytes >> 4);
     const uint32_t dh_step = p.gemm ? 0u : (uint32_t)(p.pitch * (ROW_BYTES / 16));
-    const int ndw_in = p.gemm ? 1 : ((p.ndw == 1) ? 3 : 1);   // dw taps served from one A box
-    const int ndh_in = p.gemm ? p.ncol : 3;                   // gemm: the "dh" loop walks the column tiles (A does not move)
+    const int ndw_in = p.mode ? 2 : p.gemm ? 1 : ((p.ndw == 1) ? 3 : 1);   // dw taps served from one A box
+    const int ndh_in = p.mode ? 2 : p.gemm ? p.ncol : 3;      // gemm: the "dh" loop walks the column tiles (A does not move)
     const uint32_t col_step = p.gemm ? (uint32_t)(p.S * N) : 0u;
     const int ncolt = p.gemm ? p.ncol : 1;
     int sa = 0, sb = 0, ab = 0;
@@ -400,7 +423,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         const int mu = mu_tile + s * 128 + q * 32 + lane;   // padded-flat output position inside the frame
         const int h = mu / p.pitch, w = mu - h * p.pitch;
         const bool valid = (h < p.H) && (w < p.W);
-        const size_t m = (((size_t)b * p.F + f) * p.H + h) * p.W + w;
+        const size_t m = p.mode == 2 ? (((size_t)b * p.F + f) * p.Hout + (size_t)(h * p.o_mul + p.cls_h)) * p.Wout + (w * p.o_mul + p.cls_w)
+                                     : (((size_t)b * p.F + f) * p.H + h) * p.W + w;
         float* dst = p.y + m * p.ldy + p.wrow0;
         const float* res = p.residual ? p.residual + m * p.ldy + p.wrow0 : nullptr;
 #pragma unroll
@@ -493,13 +517,14 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-static int make_act_map(CUtensorMap* m, const float* x, int B, int F, int H, int W, int C, int box_w, int box_h) {
+static int make_act_map(CUtensorMap* m, const float* x, int B, int F, int H, int W, int C, int box_w, int box_h, int estride = 1) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_err(-1, "cuTensorMapEncodeTiled unavailable", __FILE__, __LINE__);
   cuuint64_t dims[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)F, (cuuint64_t)B};
   cuuint64_t strides[4] = {(cuuint64_t)C * 4, (cuuint64_t)W * C * 4, (cuuint64_t)H * W * C * 4, (cuuint64_t)F * H * W * C * 4};
-  cuuint32_t box[5] = {(cuuint32_t)KCH, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  // estride 2: every other pixel in w and h (the box extents are in traversed elements; the tile lands compacted)
+  cuuint32_t box[5] = {(cuuint32_t)KCH, (cuuint32_t)(box_w * estride), (cuuint32_t)(box_h * estride), 1, 1};
+  cuuint32_t estr[5] = {1, (cuuint32_t)estride, (cuuint32_t)estride, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_err(-1, "cuTensorMapEncodeTiled(activation) failed", __FILE__, (int)r);
@@ -588,28 +613,40 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   // 1x1x1 conv / Linear: N tiles of 64 / 128 / 256 columns (e.g. the 384-wide qkv projection = 3 x 128)
   const bool gemm_ok = common_ok && c.ntaps == 1 && c.pt == 0 && c.ph == 0 && c.pw == 0 && c.gn_stats == nullptr &&
                        (c.Cout == 64 || c.Cout % 128 == 0) && c.Npad >= c.Cout;
-  if (!conv_ok && !gemm_ok) return -2;
+  // 1x4x4 / stride (1,2,2) / pad (0,1,1) down-conv (conv3d.py:163) and one parity class of the ConvTranspose (conv3d.py:160)
+  const bool two_ok = c.st == 1 && c.pt == 0 && c.Fo == F && c.out_layout == 0 && c.precise == 0 && c.C1 % KCH == 0 && c.C1 > 0 &&
+                      c.C2 == 0 && c.residual == nullptr && c.gn_stats == nullptr &&
+                      (c.Cout == 64 || c.Cout == 128 || c.Cout == 256) && c.Npad == c.Cout && c.Kpad == c.ntaps * c.C1;
+  const bool down_ok = two_ok && c.ntaps == 16 && c.sh == 2 && c.sw == 2 && c.ph == 1 && c.pw == 1 && c.Ho * 2 == H &&
+                       c.Wo * 2 == W && c.oh_mul == 1 && c.ow_mul == 1 && c.Hfull == c.Ho && c.Wfull == c.Wo && c.Wo >= 4 &&
+                       2 * (c.Wo + 1) <= 256;
+  const bool up_ok = two_ok && c.ntaps == 4 && c.sh == 1 && c.sw == 1 && c.Ho == H && c.Wo == W && c.oh_mul == 2 && c.ow_mul == 2 &&
+                     c.Hfull == 2 * H && c.Wfull == 2 * W && (c.oh_off == 0 || c.oh_off == 1) && (c.ow_off == 0 || c.ow_off == 1) &&
+                     c.ph == 1 - c.oh_off && c.pw == 1 - c.ow_off && W >= 4 && W + 1 <= 256;
+  if (!conv_ok && !gemm_ok && !down_ok && !up_ok) return -2;
   if (c.gn_stats && c.gn_groups != 8) return -2;   // the epilogue is specialised for GroupNorm(8), the reference default
   DPC_CHECK_ARG(c.x1 && c.w && c.y && (c.C2 == 0 || c.x2));
-  const bool gemm = !conv_ok;
+  const bool gemm = gemm_ok && !conv_ok;
+  const int mode = conv_ok || gemm_ok ? 0 : down_ok ? 1 : 2;
   // cta_group::2 pairs (two consecutive frames per cluster) for the 3x3x3 convolutions; DPC_TC_PAIR=0 disables
   const char* pair_env = getenv("DPC_TC_PAIR");          // read per call: the tests run every shape both ways
   // (W >= 32 only: with per-dw boxes the pair's lock-step exposes the A latency and measures slower than single CTAs)
-  const bool pair = !gemm && !(pair_env && atoi(pair_env) == 0) && ((int64_t)c.B * F) % 2 == 0 &&
+  const bool pair = !gemm && mode == 0 && !(pair_env && atoi(pair_env) == 0) && ((int64_t)c.B * F) % 2 == 0 &&
                     (W >= 32 || (pair_env && atoi(pair_env) == 2));
   const int Ntile = gemm ? (c.Cout == 64 ? 64 : (c.Cout == 256 ? 256 : 128)) : c.Cout;
   Params p;
   p.bias = c.bias; p.residual = c.residual; p.y = c.y; p.gn_stats = c.gn_stats; p.gn_groups = c.gn_groups;
-  p.B = c.B; p.F = F; p.H = H; p.W = W; p.C1 = c.C1; p.C2 = c.C2; p.Cout = c.Cout;
+  p.B = c.B; p.F = F; p.H = mode == 1 ? c.Ho : H; p.W = mode == 1 ? c.Wo : W; p.C1 = c.C1; p.C2 = c.C2; p.Cout = c.Cout;
+  p.mode = mode; p.cls_h = c.oh_off; p.cls_w = c.ow_off; p.Hout = c.Hfull; p.Wout = c.Wfull; p.o_mul = c.oh_mul;
   p.gemm = gemm ? 1 : 0;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DPC_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   p.ldy = c.Cout;
   p.wrow0 = 0;
   // small frames: padding columns (W+2)/W and the 128-row quantisation of the padded-flat domain waste too much of
   // the tensor pipe, so fall back to one box per dw (pitch W, three times the A traffic, zero wasted rows)
-  p.ndw = (!gemm && W >= 32) ? 1 : 3;
-  p.pitch = (p.ndw == 1) ? W + 2 : W;
-  const int frame_pos = H * p.pitch;
+  p.ndw = (mode || (!gemm && W >= 32)) ? 1 : 3;
+  p.pitch = mode ? p.W + 1 : (p.ndw == 1) ? W + 2 : W;   // 2x2 taps: one halo column
+  const int frame_pos = p.H * p.pitch;
   // gemm: up to 512 accumulator columns = ncol column tiles side by side, so A is read once for (up to) 512 outputs
   int ncol = 1;
   if (gemm) { ncol = c.Cout / Ntile; if (ncol * Ntile > 512) ncol = 512 / Ntile; }
@@ -624,7 +661,7 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   p.b_bytes = (pair ? Ntile / 2 : Ntile) * ROW_BYTES;    // a pair splits every weight box between its two CTAs
   for (;; --S) {
     // rows needed: offset inside the first row (< pitch) + S*128 positions (+ two more image rows + 2 positions of halo)
-    const int span = p.pitch - 1 + S * 128 + (gemm ? 0 : 2 * p.pitch + 2);
+    const int span = p.pitch - 1 + S * 128 + (gemm ? 0 : mode ? p.pitch + 1 : 2 * p.pitch + 2);
     p.R = (span + p.pitch - 1) / p.pitch;
     p.a_bytes = ((p.R * p.pitch * ROW_BYTES + 1023) / 1024) * 1024;
     if ((size_t)NA * p.a_bytes + 3 * (size_t)p.b_bytes + 1024 + 256 + stage_bytes <= budget || S == 1) break;
@@ -648,9 +685,10 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   const int nfull = p.R / rows_part;
   const int tail_rows = p.R - nfull * rows_part;
   CUtensorMap a1, a2, a1t, a2t, wm;
-  int rc = make_act_map(&a1, c.x1, c.B, F, H, W, c.C1, p.pitch, rows_part);
+  const int estride = mode == 1 ? 2 : 1;
+  int rc = make_act_map(&a1, c.x1, c.B, F, H, W, c.C1, p.pitch, rows_part, estride);
   if (rc) return rc;
-  rc = make_act_map(&a1t, c.x1, c.B, F, H, W, c.C1, p.pitch, tail_rows > 0 ? tail_rows : rows_part);
+  rc = make_act_map(&a1t, c.x1, c.B, F, H, W, c.C1, p.pitch, tail_rows > 0 ? tail_rows : rows_part, estride);
   if (rc) return rc;
   if (c.C2) {
     rc = make_act_map(&a2, c.x2, c.B, F, H, W, c.C2, p.pitch, rows_part);

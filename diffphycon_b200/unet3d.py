@@ -626,7 +626,7 @@ class Unet3D_with_Conv3D(nn.Module):
             skips.append((d, d_out))
             if i < n_lvl - 1:
                 e = pool.get(rows(i + 1) * d_out)
-                conv(d, d_out, P[f"downs.{i}.4.w"], P[f"downs.{i}.4.b"], e, d_out, i, "down")
+                conv(d, d_out, P[f"downs.{i}.4.w"], P[f"downs.{i}.4.b"], e, d_out, i, "down", tc=self.use_tcgen05)
                 tap(f"downs.{i}.4", e, i + 1, d_out)
                 cur, cur_c = e, d_out
             else:
@@ -660,7 +660,7 @@ class Unet3D_with_Conv3D(nn.Module):
                 e = pool.get(rows(lvl - 1) * d_in)
                 for cls in ((0, 0), (0, 1), (1, 0), (1, 1)):
                     conv(d, d_in, P[f"ups.{i}.4.w{cls[0]}{cls[1]}"], P[f"ups.{i}.4.b"], e, d_in, lvl, "up",
-                         transposed_cls=cls)
+                         transposed_cls=cls, tc=self.use_tcgen05)
                 pool.put(d)
                 tap(f"ups.{i}.4", e, lvl - 1, d_in)
                 cur, cur_c = e, d_in

@@ -177,6 +177,41 @@ def test_conv_transpose_1x4x4_four_parity_classes():
     assert rel_err(y, ref) <= TOL_TF32
 
 
+@pytest.mark.parametrize("B,Fr,H,W,C", [(2, 3, 16, 16, 64), (1, 2, 64, 64, 64), (1, 3, 32, 32, 128), (2, 1, 12, 40, 64)])
+def test_conv_down_tcgen05_parity_boxes(B, Fr, H, W, C):
+    """1x4x4 stride-2 down-conv (conv3d.py:163) on the tcgen05 kernel: four parity boxes fetched with TMA traversal stride 2,
+    2x2 taps each, against F.conv3d in fp64 (TF32 operand class)."""
+    gen = g(41)
+    x = torch.randn(B, Fr, H, W, C, generator=gen)
+    w = torch.randn(C, C, 1, 4, 4, generator=gen) / (16 * C) ** 0.5
+    bias = torch.randn(C, generator=gen)
+    ref = F.conv3d(ncdhw(x).double(), w.double(), bias.double(), stride=(1, 2, 2), padding=(0, 1, 1)).permute(0, 2, 3, 4, 1)
+    wp, _, _ = packing.pack_conv3d(w.to(DEV))
+    y, _, ran_tc = run_conv(x.to(DEV), wp, 16, bias=bias.to(DEV), cout=C, stride=(1, 2, 2), pad=(0, 1, 1), kernel=(1, 4, 4),
+                            tcgen05=True)
+    assert ran_tc, "shape should be served by the tcgen05 kernel"
+    assert y.shape == (B, Fr, H // 2, W // 2, C)
+    assert rel_err(y, ref) <= TOL_TF32
+
+
+@pytest.mark.parametrize("B,Fr,H,W,C", [(2, 3, 8, 8, 64), (1, 2, 32, 32, 64), (1, 3, 16, 16, 128), (2, 1, 6, 20, 64)])
+def test_conv_transpose_tcgen05_parity_classes(B, Fr, H, W, C):
+    """ConvTranspose3d 1x4x4 stride 2 (conv3d.py:160) as four 2x2-tap parity classes on the tcgen05 kernel (strided output)."""
+    gen = g(42)
+    x = torch.randn(B, Fr, H, W, C, generator=gen)
+    w = torch.randn(C, C, 1, 4, 4, generator=gen) / (4 * C) ** 0.5
+    bias = torch.randn(C, generator=gen)
+    ref = F.conv_transpose3d(ncdhw(x).double(), w.double(), bias.double(), stride=(1, 2, 2),
+                             padding=(0, 1, 1)).permute(0, 2, 3, 4, 1)
+    y = torch.full((B, Fr, 2 * H, 2 * W, C), float("nan"), device=DEV)
+    xd = x.to(DEV)
+    for cls, wp in packing.pack_conv_transpose_1x4x4(w.to(DEV)).items():
+        _, _, ran_tc = run_conv(xd, wp, 4, bias=bias.to(DEV), cout=C, pad=(0, 1 - cls[0], 1 - cls[1]), kernel=(1, 2, 2),
+                                up_cls=cls, y=y, tcgen05=True)
+        assert ran_tc, "shape should be served by the tcgen05 kernel"
+    assert rel_err(y, ref) <= TOL_TF32
+
+
 def test_linear_residual_and_reference_layout_output():
     gen = g(6)
     x = torch.randn(2, 3, 8, 8, 128, generator=gen)
