@@ -13,8 +13,8 @@
 //     ([Cout] x [32], K-major) is amortised over S MMA groups.
 // A traffic per tile drops from 27 box-equivalents to ~3.4; the kernel becomes tensor-pipe bound for Cout >= 64.
 //
-// Warp roles (256 threads): warp 0 = TMA producer (one elected lane), warp 1 = tcgen05.mma issuer (one lane),
-// warp 2 = TMEM allocator, warps 4-7 = epilogue (tcgen05.ld -> +bias -> GroupNorm partial statistics -> global store).
+// Warp roles (384 threads): warp 0 = weight TMA producer (one lane), warp 3 = activation TMA producer (one lane), warp 1 =
+// tcgen05.mma issuer (one lane), warp 2 = TMEM allocator, warps 4-11 = epilogue (tcgen05.ld -> +bias -> GroupNorm partial statistics -> global store).
 // Two mbarrier rings: A boxes (2 deep) and weight boxes (NB deep); tcgen05.commit releases slots and publishes the
 // finished accumulators.  Every wait is bounded (trap after ~2 s) so a protocol bug cannot hang the device.
 #include "tc_common.cuh"
@@ -159,66 +159,62 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------- TMA producer -------------------------------------------
-    // Issue order follows slot availability: the weight boxes of block j that fit the ring go first, then the A box of
-    // the next block (its buffer frees when block j-1 retires) cut into APARTS row slabs interleaved with the remaining
-    // weight boxes, so a 90 KB A transfer never sits in front of a weight box the tensor pipe is about to need.
+  if (warp == 3 && lane == 0) {
+    // ------------------------------------------- TMA producer: activations -------------------------------
+    // Own thread (the weight stream below blocks on its own ring): the A box of a block is fetched as APARTS row slabs as
+    // soon as its slot frees, up to NA blocks ahead of the MMAs.
     const int rows_part = (p.R + APARTS - 1) / APARTS;
-    int sa = 0, sb = 0;
-    uint32_t pha = 1, phb = 1;                            // producer parity: first pass over a fresh ring does not block
-    // state of the A box being fetched (one block ahead of the weight stream)
-    int a_it = it_begin, a_blk = 0, a_part = 0, a_cnt = 0, b_cnt = 0;
-    const uint32_t fullA_l = PAIR ? leader_addr(fullA) : fullA, fullB_l = PAIR ? leader_addr(fullB) : fullB;
-    const int brow = PAIR ? (int)cta_rank * (N / 2) : 0;   // this CTA's half of the weight rows
-    auto issue_a_part = [&]() {
-      if (a_it >= it_end) return;
+    int sa = 0;
+    uint32_t pha = 1;                                     // producer parity: first pass over a fresh ring does not block
+    int a_cnt = 0;
+    const uint32_t fullA_l = PAIR ? leader_addr(fullA) : fullA;
+    for (int a_it = it_begin; a_it < it_end; a_it += it_step) {
       const int a_tile = tile_of(a_it);
       const int tf = a_tile % p.tiles_f;
       const int f = (a_tile / p.tiles_f) % p.F;
       const int b = a_tile / (p.tiles_f * p.F);
       const int hq = (tf * p.S * 128) / p.pitch;
-      int dt = 1, ch = a_blk, dwb = 1, halo = 0;             // gemm: centre tap only, no halo
-      int w0 = 0, h0 = 0;
-      if (p.mode == 1) {                                     // parity box (ph, pw): input rows 2h + ph - 1 + 2*{0,1}, same in w
-        const int par = a_blk / nch;
-        ch = a_blk - par * nch;
-        h0 = 2 * hq + ((par >> 1) ? -1 : 0);
-        w0 = (par & 1) ? -1 : 0;
-      } else if (p.mode == 2) {                              // class (cls_h, cls_w): input rows h - (1 - cls_h) + {0,1}
-        h0 = hq - (1 - p.cls_h);
-        w0 = -(1 - p.cls_w);
-      } else if (!p.gemm) {
-        dt = a_blk / (nch * p.ndw);
-        const int rem = a_blk - dt * nch * p.ndw;
-        ch = rem / p.ndw;
-        dwb = rem - ch * p.ndw;
-        halo = 1;
-      }
-      const bool src1 = ch < nch1;
-      const int c0 = src1 ? ch * KCH : (ch - nch1) * KCH;
-      const int r0 = a_part * rows_part;
-      if (a_part == 0) {
+      for (int a_blk = 0; a_blk < nblk; ++a_blk, ++a_cnt) {
+        int dt = 1, ch = a_blk, dwb = 1, halo = 0;           // gemm: centre tap only, no halo
+        int w0 = 0, h0 = 0;
+        if (p.mode == 1) {                                   // parity box (ph, pw): input rows 2h + ph - 1 + 2*{0,1}, same in w
+          const int par = a_blk / nch;
+          ch = a_blk - par * nch;
+          h0 = 2 * hq + ((par >> 1) ? -1 : 0);
+          w0 = (par & 1) ? -1 : 0;
+        } else if (p.mode == 2) {                            // class (cls_h, cls_w): input rows h - (1 - cls_h) + {0,1}
+          h0 = hq - (1 - p.cls_h);
+          w0 = -(1 - p.cls_w);
+        } else if (!p.gemm) {
+          dt = a_blk / (nch * p.ndw);
+          const int rem = a_blk - dt * nch * p.ndw;
+          ch = rem / p.ndw;
+          dwb = rem - ch * p.ndw;
+          halo = 1;
+        }
+        const bool src1 = ch < nch1;
+        const int c0 = src1 ? ch * KCH : (ch - nch1) * KCH;
         mbar_wait(emptyA + 8 * sa, pha);
+        const bool skip = !PAIR && (p.dbg & 2) && a_cnt >= NA;
         if (PAIR) { if (leader) mbar_expect_tx(fullA + 8 * sa, (uint32_t)(2 * p.R * p.pitch * ROW_BYTES)); }
-        else if ((p.dbg & 2) && a_cnt >= NA) mbar_arrive(fullA + 8 * sa);
+        else if (skip) mbar_arrive(fullA + 8 * sa);
         else mbar_expect_tx(fullA + 8 * sa, (uint32_t)(p.R * p.pitch * ROW_BYTES));
-      }
-      if (r0 < p.R && !(!PAIR && (p.dbg & 2) && a_cnt >= NA)) {
-        const CUtensorMap* mp = (r0 + rows_part <= p.R) ? (src1 ? &tmA1 : &tmA2) : (src1 ? &tmA1t : &tmA2t);
-        const uint32_t dst = a_buf + sa * p.a_bytes + (uint32_t)(r0 * p.pitch * ROW_BYTES);
-        if (p.mode) tma_load_5d(dst, mp, fullA + 8 * sa, c0, w0, h0 + (p.mode == 1 ? 2 * r0 : r0), f, b);
-        else if (PAIR) tma_load_5d_pair(dst, mp, fullA_l + 8 * sa, c0, dwb - 1, hq - halo + r0, f + dt - 1, b);
-        else tma_load_5d(dst, mp, fullA + 8 * sa, c0, dwb - 1, hq - halo + r0, f + dt - 1, b);
-      }
-      if (++a_part == APARTS) {
-        a_part = 0;
-        ++a_cnt;
+        for (int r0 = 0; r0 < p.R && !skip; r0 += rows_part) {
+          const CUtensorMap* mp = (r0 + rows_part <= p.R) ? (src1 ? &tmA1 : &tmA2) : (src1 ? &tmA1t : &tmA2t);
+          const uint32_t dst = a_buf + sa * p.a_bytes + (uint32_t)(r0 * p.pitch * ROW_BYTES);
+          if (p.mode) tma_load_5d(dst, mp, fullA + 8 * sa, c0, w0, h0 + (p.mode == 1 ? 2 * r0 : r0), f, b);
+          else if (PAIR) tma_load_5d_pair(dst, mp, fullA_l + 8 * sa, c0, dwb - 1, hq - halo + r0, f + dt - 1, b);
+          else tma_load_5d(dst, mp, fullA + 8 * sa, c0, dwb - 1, hq - halo + r0, f + dt - 1, b);
+        }
         if (++sa == NA) { sa = 0; pha ^= 1; }
-        if (++a_blk == nblk) { a_blk = 0; a_it += it_step; }
       }
-    };
-    for (int i = 0; i < (NA - 1) * APARTS; ++i) issue_a_part();   // the A stream runs NA-1 blocks ahead of the weight stream
+    }
+  } else if (warp == 0 && lane == 0) {
+    // ------------------------------------------- TMA producer: weights ----------------------------------
+    int sb = 0, b_cnt = 0;
+    uint32_t phb = 1;
+    const uint32_t fullB_l = PAIR ? leader_addr(fullB) : fullB;
+    const int brow = PAIR ? (int)cta_rank * (N / 2) : 0;   // this CTA's half of the weight rows
     for (int it = it_begin; it < it_end; it += it_step) {
       for (int j = 0; j < nblk; ++j) {
         int dt = 0, ch = j, dwb = 0;
@@ -235,7 +231,6 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         // weight column of tap (dt, dh, dw): ((dt*3 + dh)*3 + dw)*Cin + ch*32; per box either all nine (dh,dw) or the three dh
         const int k0 = p.gemm ? ch * KCH : (dt * 9 + dwb) * Cin + ch * KCH;
         const int kstep = (p.ndw == 1) ? Cin : 3 * Cin;
-        int parts_left = APARTS;
         for (int t = 0; t < ntap; ++t) {
           mbar_wait(emptyB + 8 * sb, phb);
           if (PAIR) {
@@ -253,9 +248,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           }
           ++b_cnt;
           if (++sb == p.NB) { sb = 0; phb ^= 1; }
-          if ((t + 2 >= p.NB || t + 1 >= ntap - 1) && parts_left > 0) { issue_a_part(); --parts_left; }
         }
-        while (parts_left > 0) { issue_a_part(); --parts_left; }
       }
     }
   } else if (warp == 1 && leader) {
