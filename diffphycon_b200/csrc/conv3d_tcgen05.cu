@@ -48,6 +48,7 @@ struct Params {
                               // stride 2, 2x2 taps each); 2: one parity class of the 1x4x4 stride-2 ConvTranspose (2x2 taps)
   int cls_h, cls_w;           // mode 2: output parity class
   int Hout, Wout, o_mul;      // output frame and position scale: out(h, w) -> (h*o_mul + cls_h, w*o_mul + cls_w)
+  int staged;                 // conv epilogue: stores staged through shared memory (128-byte row segments)
   int dbg;                    // DPC_TC_DEBUG experiment switches (1: weight boxes fetched once, 2: A boxes fetched once)
 };
 
@@ -109,7 +110,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   const uint32_t fullB = bars + 16 * NA, emptyB = fullB + 8 * p.NB;
   const uint32_t acc_full = emptyB + 8 * p.NB, acc_empty = acc_full + 16;
   const uint32_t tmem_slot = acc_empty + 16;
-  float* stage_all = reinterpret_cast<float*>(smem_raw + (base - raw) + NA * p.a_bytes + p.NB * p.b_bytes + 256);  // gemm mode only
+  float* stage_all = reinterpret_cast<float*>(smem_raw + (base - raw) + NA * p.a_bytes + p.NB * p.b_bytes + 256);  // epilogue staging tiles
   __shared__ double s_part[8][16];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -413,13 +414,33 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         }
       } else
       for (int s = eg; s < nsub; s += 2) {
-        const int mu = mu_tile + s * 128 + q * 32 + lane;   // padded-flat output position inside the frame
-        const int h = mu / p.pitch, w = mu - h * p.pitch;
-        const bool valid = (h < p.H) && (w < p.W);
-        const size_t m = p.mode == 2 ? (((size_t)b * p.F + f) * p.Hout + (size_t)(h * p.o_mul + p.cls_h)) * p.Wout + (w * p.o_mul + p.cls_w)
-                                     : (((size_t)b * p.F + f) * p.H + h) * p.W + w;
+        const int mu_w = mu_tile + s * 128 + q * 32;        // first padded-flat position of this warp's 32 rows
+        const size_t bf = (size_t)b * p.F + f;
+        auto out_row = [&](int mu, bool& ok) -> size_t {     // output row index of position mu
+          const int h = mu / p.pitch, w = mu - h * p.pitch;
+          ok = (h < p.H) && (w < p.W);
+          return p.mode == 2 ? (bf * p.Hout + (size_t)(h * p.o_mul + p.cls_h)) * p.Wout + (w * p.o_mul + p.cls_w)
+                             : (bf * p.H + h) * p.W + w;
+        };
+        bool valid;
+        const size_t m = out_row(mu_w + lane, valid);
+        // staged stores: the warp's 32 rows x 32 columns go through a shared-memory tile and leave as 128-byte row segments
+        // (a warp store covers 4 rows x 128 B instead of 32 rows x 16 B: 8x fewer L1 transactions; the direct form costs
+        // ~12K clk per 384 x 128 tile, which is exposed whenever the accumulators are single-buffered)
+        float* stage = stage_all + (warp - 4) * (32 * 36);
+        const int rsub = lane >> 3, cq = (lane & 7) * 4;
+        uint32_t roff[8];
+        uint32_t vmask = 0;
+        if (p.staged) {
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            bool ok;
+            const size_t mr = out_row(mu_w + it * 4 + rsub, ok);
+            roff[it] = (uint32_t)(mr * (size_t)p.ldy) + (uint32_t)(p.wrow0 + cq);
+            vmask |= ok ? (1u << it) : 0u;
+          }
+        }
         float* dst = p.y + m * p.ldy + p.wrow0;
-        const float* res = p.residual ? p.residual + m * p.ldy + p.wrow0 : nullptr;
 #pragma unroll
         for (int c = 0; c < N / 32; ++c) {
           uint32_t v[32];
@@ -435,29 +456,33 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             o[j + 2] = __uint_as_float(v[j + 2]) + bv.z;
             o[j + 3] = __uint_as_float(v[j + 3]) + bv.w;
           }
-          if (valid) {
-            if (res) {
+          if (p.staged) {
 #pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 rv = __ldcs(reinterpret_cast<const float4*>(res + c * 32 + j));
-                o[j] += rv.x; o[j + 1] += rv.y; o[j + 2] += rv.z; o[j + 3] += rv.w;
-              }
-            }
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(stage + lane * 36 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              if ((vmask >> it) & 1u)
+                __stcs(reinterpret_cast<float4*>(p.y + roff[it] + c * 32),
+                       *reinterpret_cast<const float4*>(stage + (it * 4 + rsub) * 36 + cq));
+            __syncwarp();
+          } else if (valid) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               __stcs(reinterpret_cast<float4*>(dst + c * 32 + j), make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]));
-            if (do_stats) {
+          }
+          if (valid && do_stats) {
 #pragma unroll
-              for (int g = 0; g < GPC; ++g) {
-                float ps = 0.f, pq = 0.f;
+            for (int g = 0; g < GPC; ++g) {
+              float ps = 0.f, pq = 0.f;
 #pragma unroll
-                for (int j = 0; j < GW; ++j) {
-                  ps += o[g * GW + j];
-                  pq = fmaf(o[g * GW + j], o[g * GW + j], pq);
-                }
-                fs[(c * GPC + g) % 8] += ps;              // (c*GPC + g) < 8 by construction
-                fq[(c * GPC + g) % 8] += pq;
+              for (int j = 0; j < GW; ++j) {
+                ps += o[g * GW + j];
+                pq = fmaf(o[g * GW + j], o[g * GW + j], pq);
               }
+              fs[(c * GPC + g) % 8] += ps;              // (c*GPC + g) < 8 by construction
+              fq[(c * GPC + g) % 8] += pq;
             }
           }
         }
@@ -623,9 +648,7 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   const int mode = conv_ok || gemm_ok ? 0 : down_ok ? 1 : 2;
   // cta_group::2 pairs (two consecutive frames per cluster) for the 3x3x3 convolutions; DPC_TC_PAIR=0 disables
   const char* pair_env = getenv("DPC_TC_PAIR");          // read per call: the tests run every shape both ways
-  // (W >= 32 only: with per-dw boxes the pair's lock-step exposes the A latency and measures slower than single CTAs)
-  const bool pair = !gemm && mode == 0 && !(pair_env && atoi(pair_env) == 0) && ((int64_t)c.B * F) % 2 == 0 &&
-                    (W >= 32 || (pair_env && atoi(pair_env) == 2));
+  const bool pair = !gemm && mode == 0 && !(pair_env && atoi(pair_env) == 0) && ((int64_t)c.B * F) % 2 == 0;
   const int Ntile = gemm ? (c.Cout == 64 ? 64 : (c.Cout == 256 ? 256 : 128)) : c.Cout;
   Params p;
   p.bias = c.bias; p.residual = c.residual; p.y = c.y; p.gn_stats = c.gn_stats; p.gn_groups = c.gn_groups;
@@ -649,7 +672,8 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   if (S > MAXS) S = MAXS;
   if (S > (frame_pos + 127) / 128) S = (frame_pos + 127) / 128;
   const size_t budget = 227 * 1024 - 2048;
-  const size_t stage_bytes = gemm ? (size_t)8 * 32 * 36 * sizeof(float) : 0;
+  const size_t stage_full = (size_t)8 * 32 * 36 * sizeof(float);
+  size_t stage_bytes = gemm ? stage_full : 0;
   int NA = 2;
   p.b_bytes = (pair ? Ntile / 2 : Ntile) * ROW_BYTES;    // a pair splits every weight box between its two CTAs
   for (;; --S) {
@@ -660,9 +684,27 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
     if ((size_t)NA * p.a_bytes + 3 * (size_t)p.b_bytes + 1024 + 256 + stage_bytes <= budget || S == 1) break;
   }
   if ((size_t)NA * p.a_bytes + 3 * (size_t)p.b_bytes + 1024 + 256 + stage_bytes > budget || p.R > 256) return -2;
-  // per-dw boxes serve only three taps each: a third slot keeps two of them in flight behind the one being multiplied
-  if (!gemm && p.ndw == 3 && (size_t)3 * p.a_bytes + 3 * (size_t)p.b_bytes + 1024 + 256 <= budget) NA = 3;
-  { static int na_dbg = -1; if (na_dbg < 0) { const char* e = getenv("DPC_TC_NA"); na_dbg = e ? atoi(e) : 0; } if (na_dbg) NA = na_dbg; }
+  // balance the sub-tiles over the tiles of a frame (e.g. 32x34 positions = 9 sub-tiles: 3+3+3 instead of 4+4+1 — a tile
+  // with one sub-tile still streams every weight box)
+  if (!gemm) {
+    const int nsub_total = (frame_pos + 127) / 128, nt = (nsub_total + S - 1) / S;
+    const int Sb = (nsub_total + nt - 1) / nt;
+    if (Sb < S) {
+      S = Sb;
+      const int span = p.pitch - 1 + S * 128 + (mode ? p.pitch + 1 : 2 * p.pitch + 2);
+      p.R = (span + p.pitch - 1) / p.pitch;
+      p.a_bytes = ((p.R * p.pitch * ROW_BYTES + 1023) / 1024) * 1024;
+    }
+  }
+  // conv epilogue staging tiles when they leave >= 4 weight slots (and 32-bit element offsets suffice)
+  p.staged = 0;
+  if (!gemm && (size_t)NA * p.a_bytes + 4 * (size_t)p.b_bytes + 1024 + 256 + stage_full <= budget &&
+      (int64_t)c.B * F * c.Hfull * c.Wfull * c.Cout < ((int64_t)1 << 32)) {
+    p.staged = 1;
+    stage_bytes = stage_full;
+  }
+  // a third A slot (two boxes in flight behind the one being multiplied) whenever it leaves >= 4 weight slots
+  if (!gemm && (size_t)3 * p.a_bytes + 4 * (size_t)p.b_bytes + 1024 + 256 + stage_bytes <= budget) NA = 3;
   p.NA = NA;
   p.S = S;
   p.AB = (2 * S * ncol * Ntile <= 512) ? 2 : 1;

@@ -416,9 +416,9 @@ TC_CASES = [
 @pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
 def test_conv3d_tcgen05(case, pair, monkeypatch):
     """The TMA/tcgen05 kernel against fp64 conv3d and against the generic tensor-core kernel (same numerics class).
-    cta_pair: cta_group::2 clusters (taken when B*F is even); single_cta: DPC_TC_PAIR=0 forces one CTA per tile."""
+    cta_pair: cta_group::2 clusters (the default when B*F is even); single_cta: DPC_TC_PAIR=0 forces one CTA per tile."""
     _, B, Fr, H, W, C1, C2, Cout = case
-    monkeypatch.setenv("DPC_TC_PAIR", "2" if pair else "0")   # 2: pairs for small frames too (default: W >= 32 only)
+    monkeypatch.setenv("DPC_TC_PAIR", "1" if pair else "0")
     gen = g(21)
     x1 = torch.randn(B, Fr, H, W, C1, generator=gen)
     x2 = torch.randn(B, Fr, H, W, C2, generator=gen) if C2 else None
