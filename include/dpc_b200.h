@@ -71,13 +71,20 @@ typedef struct dpc_conv_params {
 
 int dpc_conv_igemm(const dpc_conv_params* p, void* stream);
 
-/* Conv3d 3x3x3 / pad 1 and 1x1x1 (= Linear over channels-last rows) on the 5th-generation tensor cores: persistent CTAs,
- * TMA-tiled operand staging (3x3x3: one halo box per (dt, 32-channel chunk) shared by all nine in-plane taps),
- * tcgen05.mma kind::tf32, accumulators double-buffered in TMEM.  Same arguments, weight packing and epilogue as
- * dpc_conv_igemm (bias, residual for 1x1x1, GroupNorm(8) partial statistics for 3x3x3).
- * Supported: unit stride, channels-last output, C1 % 32 == 0, C2 % 32 == 0, 4 <= W <= 254, precise == 0, and
- *   ntaps == 27: pad 1, no residual, Cout in {64,128,256} == Npad, gn_groups in {0, 8};
- *   ntaps == 1 : pad 0, no gn_stats, Cout == 64 or Cout % 128 == 0 (run as column tiles of 64/128/256).
+/* Conv3d 3x3x3 / pad 1, 1x1x1 (= Linear over channels-last rows), the 1x4x4 stride-(1,2,2) down-conv and one parity class of
+ * the 1x4x4 stride-(1,2,2) ConvTranspose on the 5th-generation tensor cores: persistent CTAs, TMA-tiled operand staging
+ * (3x3x3: one halo box per (dt, 32-channel chunk) shared by all nine in-plane taps; down-conv: four parity boxes fetched with
+ * TMA traversal stride 2), tcgen05.mma kind::tf32, accumulators in TMEM (double-buffered when they fit).  When B*F is even the
+ * 3x3x3 path runs as cta_group::2 clusters (two consecutive frames per CTA pair, M = 256 MMAs; DPC_TC_PAIR=0 disables).
+ * Same arguments, weight packing and epilogue as dpc_conv_igemm (bias, residual for 1x1x1, GroupNorm(8) partial statistics
+ * for 3x3x3).
+ * Supported: channels-last output, C1 % 32 == 0, C2 % 32 == 0, 4 <= W <= 254, precise == 0, and
+ *   ntaps == 27: unit stride, pad 1, no residual, Cout in {64,128,256} == Npad, gn_groups in {0, 8};
+ *   ntaps == 1 : unit stride, pad 0, no gn_stats, Cout == 64 or Cout % 128 == 0 (column tiles of 64/128/256, up to 512
+ *                outputs per pass over the input);
+ *   ntaps == 16: kernel 1x4x4, stride (1,2,2), pad (0,1,1), C2 == 0, Cout in {64,128,256} == Npad, no residual / gn_stats;
+ *   ntaps == 4 : kernel 1x2x2 of ConvTranspose parity class (oh_off, ow_off), ph == 1-oh_off, pw == 1-ow_off,
+ *                oh_mul == ow_mul == 2, same channel constraints.
  * Returns -2 (nothing launched) for any other shape so the host mirror can use dpc_conv_igemm (same numerics class). */
 int dpc_conv3d_tcgen05(const dpc_conv_params* p, void* stream);
 

@@ -176,6 +176,19 @@ def spatial_linear_attention(qkv, ctx_ws, out, BF, HW, heads):
     out[: o.numel()] = o.reshape(-1)
 
 
+def stem_conv(x, w, bias, y, B, F, H, W, Cpad, N, kt, kh, kw):
+    """dpc_stem_conv_tcgen05: unpacks the [N][kt*kh*P*32] sliding-window weight layout (packing.pack_stem_conv) and runs the
+    convolution in fp64."""
+    if Cpad % 4 or Cpad > 16 or N not in (32, 64, 128) or kw != 7 or W < 8:
+        return False
+    P = Cpad // 4
+    wt = w[: N * kt * kh * P * 32].reshape(N, kt, kh, P, 8, 4).permute(0, 3, 5, 1, 2, 4).reshape(N, Cpad, kt, kh, 8)[..., :7]
+    xin = x[: B * F * H * W * Cpad].reshape(B, F, H, W, Cpad).permute(0, 4, 1, 2, 3)
+    o = torch.nn.functional.conv3d(xin.double(), wt.double(), bias.double(), padding=(kt // 2, kh // 2, 3))
+    y[: B * F * H * W * N] = o.permute(0, 2, 3, 4, 1).float().reshape(-1)
+    return True
+
+
 def spatial_linear_block_fused(x, w_qkv, w_out, b_out, ctx_ws, mt_ws, y, BF, HW, Cn, heads, eps=1e-5):
     if Cn != 64 or heads != 4 or HW % 128:
         return False
@@ -321,7 +334,7 @@ def jelly_write_bd(pred_bd, bd_0, x_next, x_w, cond_steps):
     x_w[:, :, 3:6] = bd
 
 
-EMULATED = ("temporal_block_fused", "jelly_x_start", "jelly_step", "jelly_write_bd", "burgers_model_output", "ddpm_posterior_step", "conv", "groupnorm_silu", "layernorm_channels", "pack_input", "temporal_attention", "spatial_attention",
+EMULATED = ("temporal_block_fused", "spatial_linear_block_fused", "stem_conv", "jelly_x_start", "jelly_step", "jelly_write_bd", "burgers_model_output", "ddpm_posterior_step", "conv", "groupnorm_silu", "layernorm_channels", "pack_input", "temporal_attention", "spatial_attention",
             "spatial_linear_attention", "time_embed", "time_proj", "predict_x_start", "guided_step", "upsample_nearest2x")
 
 
