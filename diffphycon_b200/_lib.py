@@ -66,6 +66,8 @@ _SIGNATURES = {
     "dpc_spatial_attention": ([c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_spatial_linear_block_fused": ([c_fp] * 7 + [C.c_int32] * 4 + [C.c_float, c_fp], C.c_int),
     "dpc_stem_conv_tcgen05": ([c_fp] * 4 + [C.c_int32] * 9 + [c_fp], C.c_int),
+    "dpc_final_proj": ([c_fp] * 4 + [C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
+    "dpc_spatial_attention_mma": ([c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_spatial_linear_attention": ([c_fp, c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_time_embed": ([c_fp] * 8 + [C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_time_proj": ([c_fp] * 4 + [C.c_int32] * 3 + [c_fp], C.c_int),
@@ -238,9 +240,27 @@ def temporal_block_fused(x, w_qkv, w_out, rope_cos, rope_sin, pos_bias, y, B, F,
 
 
 @_timed("spatial_attention")
-def spatial_attention(qkv, out, BF, HW, heads):
+def spatial_attention(qkv, out, BF, HW, heads, precise=True):
+    """precise=False: q k^T and P v as TF32 tensor-core MMAs (dpc_spatial_attention_mma) when the shape is served."""
+    if not precise:
+        rc = lib().dpc_spatial_attention_mma(ptr(qkv), ptr(out), BF, HW, heads, stream_ptr())
+        if rc != -2:
+            check(rc, "dpc_spatial_attention_mma")
+            LaunchCounter.count += 1
+            return
     check(lib().dpc_spatial_attention(ptr(qkv), ptr(out), BF, HW, heads, stream_ptr()), "dpc_spatial_attention")
     LaunchCounter.count += 1
+
+
+@_timed("final_proj")
+def final_proj(x, w, bias, out, BF, HW, Cn, Cout) -> bool:
+    """final 1x1x1 conv to <= 6 channels in the reference layout; False if the shape is not served (-2)."""
+    rc = lib().dpc_final_proj(ptr(x), ptr(w), ptr(bias), ptr(out), BF, HW, Cn, Cout, stream_ptr())
+    if rc == -2:
+        return False
+    check(rc, "dpc_final_proj")
+    LaunchCounter.count += 1
+    return True
 
 
 @_timed("stem_conv_tcgen05")

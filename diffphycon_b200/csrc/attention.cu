@@ -343,6 +343,143 @@ temporal_attention_mma_kernel(const float* __restrict__ qkv, const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// mid-block spatial softmax attention on tensor cores (TF32 mma.sync m16n8k8, flash-attention style): one CTA per
+// (frame, head, block of 256 queries), a warp owns 32 queries (two m16 tiles); K/V stream through shared memory in blocks
+// of 64 keys with an online softmax; the score accumulators are re-used as the A operand of P.V through the k-index
+// permutation (keys 2t, 2t+1 <-> k positions t, t+4), so P never leaves the registers.  Shared rows have pitch 36 floats:
+// both B-fragment access patterns (K: row g, column t; V: row 2t, column g) are bank-conflict free.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+spatial_attention_mma_kernel(const float* __restrict__ qkv, float* __restrict__ out, int HW, int heads) {
+  constexpr int KB = 64, PITCH = 36;
+  __shared__ __align__(16) float Ks[KB * PITCH];
+  __shared__ __align__(16) float Vs[KB * PITCH];
+  const int head = blockIdx.y;
+  const int64_t bf = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int C3 = 3 * heads * DH, hid = heads * DH;
+  const float* base = qkv + (size_t)bf * HW * C3 + head * DH;
+  const int q0 = blockIdx.x * 256 + warp * 32;           // first query of this warp
+  const bool active = q0 < HW;                           // HW % 32 == 0: a warp is entirely in or out
+  // Q fragments, scaled, TF32: qa[mt][kk] = rows q0 + 16 mt + {g, g+8}, columns 8 kk + {t, t+4}
+  uint32_t qa[2][4][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int row = q0 + 16 * mt + g + 8 * (e & 1), col = 8 * kk + t + 4 * (e >> 1);
+        qa[mt][kk][e] = active ? to_tf32(__fmul_rn(__ldg(base + (size_t)row * C3 + col), ATT_SCALE)) : 0u;
+      }
+  float oc[2][4][4];
+  float mx[2][2], l[2][2];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt) {
+#pragma unroll
+    for (int dn = 0; dn < 4; ++dn)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) oc[mt][dn][e] = 0.f;
+    mx[mt][0] = mx[mt][1] = -INFINITY;
+    l[mt][0] = l[mt][1] = 0.f;
+  }
+  for (int j0 = 0; j0 < HW; j0 += KB) {
+    __syncthreads();
+    // 64 keys x (32 k + 32 v) floats = 1024 float4, 4 per thread; TF32-rounded once here
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = threadIdx.x + 256 * i;
+      const int tk = idx >> 4, part = idx & 15;
+      const float4 v = __ldg(reinterpret_cast<const float4*>(base + (size_t)(j0 + tk) * C3 + (part < 8 ? hid : 2 * hid) + (part & 7) * 4));
+      float* dst = (part < 8 ? Ks : Vs) + tk * PITCH + (part & 7) * 4;
+      *reinterpret_cast<float4*>(dst) = make_float4(__uint_as_float(to_tf32(v.x)), __uint_as_float(to_tf32(v.y)),
+                                                    __uint_as_float(to_tf32(v.z)), __uint_as_float(to_tf32(v.w)));
+    }
+    __syncthreads();
+    if (!active) continue;
+    // ---- S = q K^T for 64 keys ----
+    float sc[2][8][4];
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) sc[mt][nt][e] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const uint32_t b0 = __float_as_uint(Ks[(8 * nt + g) * PITCH + 8 * kk + t]);
+        const uint32_t b1 = __float_as_uint(Ks[(8 * nt + g) * PITCH + 8 * kk + t + 4]);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) mma_tf32_16x8x8(sc[mt][nt], qa[mt][kk], b0, b1);
+      }
+    // ---- online softmax: rows 16 mt + g (elements 0,1) and + 8 (elements 2,3) ----
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int e2 = 0; e2 < 2; ++e2) {
+        float tm = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) tm = fmaxf(tm, fmaxf(sc[mt][nt][2 * e2], sc[mt][nt][2 * e2 + 1]));
+        tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, 1));
+        tm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, 2));
+        const float nm = fmaxf(mx[mt][e2], tm);
+        const float corr = __expf(mx[mt][e2] - nm);      // first block: exp(-inf) = 0
+        mx[mt][e2] = nm;
+        float ps = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+          const float p0 = __expf(sc[mt][nt][2 * e2] - nm), p1 = __expf(sc[mt][nt][2 * e2 + 1] - nm);
+          sc[mt][nt][2 * e2] = p0;
+          sc[mt][nt][2 * e2 + 1] = p1;
+          ps += p0 + p1;
+        }
+        l[mt][e2] = l[mt][e2] * corr + ps;               // this lane's share of the row sum (reduced over the quad at the end)
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn) {
+          oc[mt][dn][2 * e2] *= corr;
+          oc[mt][dn][2 * e2 + 1] *= corr;
+        }
+      }
+    // ---- O += P V: score fragments are the A operand (k positions t, t+4 <-> keys 8 kb + 2t, 2t+1) ----
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+      uint32_t pa[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt) {
+        pa[mt][0] = to_tf32(sc[mt][kb][0]);              // (row g,   key 2t)
+        pa[mt][1] = to_tf32(sc[mt][kb][2]);              // (row g+8, key 2t)
+        pa[mt][2] = to_tf32(sc[mt][kb][1]);              // (row g,   key 2t+1)
+        pa[mt][3] = to_tf32(sc[mt][kb][3]);              // (row g+8, key 2t+1)
+      }
+#pragma unroll
+      for (int dn = 0; dn < 4; ++dn) {
+        const uint32_t b0 = __float_as_uint(Vs[(8 * kb + 2 * t) * PITCH + 8 * dn + g]);
+        const uint32_t b1 = __float_as_uint(Vs[(8 * kb + 2 * t + 1) * PITCH + 8 * dn + g]);
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) mma_tf32_16x8x8(oc[mt][dn], pa[mt], b0, b1);
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+      for (int e2 = 0; e2 < 2; ++e2) {
+        float ls = l[mt][e2];
+        ls += __shfl_xor_sync(0xffffffffu, ls, 1);
+        ls += __shfl_xor_sync(0xffffffffu, ls, 2);
+        const float inv = 1.0f / ls;
+        float* orow = out + ((size_t)bf * HW + q0 + 16 * mt + g + 8 * e2) * hid + head * DH;
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn)
+          *reinterpret_cast<float2*>(orow + 8 * dn + 2 * t) = make_float2(oc[mt][dn][2 * e2] * inv, oc[mt][dn][2 * e2 + 1] * inv);
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // mid-block spatial softmax attention: one thread per query token, K/V streamed through shared memory in tiles of 32
 // tokens with an online softmax.  grid = (ceil(HW/128), heads, B*F).
 // ------------------------------------------------------------------------------------------------------------
@@ -638,6 +775,16 @@ extern "C" int dpc_spatial_attention(const float* qkv, float* out, int32_t BF, i
   DPC_CHECK_ARG(qkv && out && BF > 0 && BF <= 65535 && HW > 0 && heads > 0);
   dim3 grid((unsigned)((HW + 127) / 128), (unsigned)heads, (unsigned)BF);
   spatial_attention_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(qkv, out, HW, heads);
+  DPC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dpc_spatial_attention_mma(const float* qkv, float* out, int32_t BF, int32_t HW, int32_t heads, void* stream) {
+  using namespace dpc;
+  if (HW % 64 != 0) return -2;                            // served by dpc_spatial_attention (fp32 SIMT)
+  DPC_CHECK_ARG(qkv && out && BF > 0 && BF <= 65535 && HW > 0 && heads > 0);
+  dim3 grid((unsigned)((HW + 255) / 256), (unsigned)heads, (unsigned)BF);
+  spatial_attention_mma_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(qkv, out, HW, heads);
   DPC_LAUNCH_CHECK();
   return 0;
 }

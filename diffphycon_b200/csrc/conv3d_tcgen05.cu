@@ -83,6 +83,30 @@ __device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_c, uint64_t adesc, 
       ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Descriptors passed as (low word, high word): the per-MMA arithmetic only moves the 14-bit start-address field of the low
+// word, so the single issuing thread does 32-bit adds instead of 64-bit ones (it has ~32 clk per N = 64 instruction).
+template <bool PAIR>
+__device__ __forceinline__ void umma_tf32_w(uint32_t tmem_c, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+  if (PAIR)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_c), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_c), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(bar), "h"((uint16_t)3) : "memory");
@@ -262,6 +286,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
                            ((uint32_t)((PAIR ? 256 : 128) >> 4) << 24);
     const uint64_t adesc_buf0 = umma_desc(a_buf);
     const uint64_t bdesc_buf0 = umma_desc(b_buf);
+    const uint32_t a_lo0 = (uint32_t)adesc_buf0, a_hi = (uint32_t)(adesc_buf0 >> 32);
+    const uint32_t b_lo0 = (uint32_t)bdesc_buf0, b_hi = (uint32_t)(bdesc_buf0 >> 32);
     const uint32_t a_step = (uint32_t)(p.a_bytes >> 4), b_step = (uint32_t)(p.b_bytes >> 4);
     const uint32_t dh_step = p.gemm ? 0u : (uint32_t)(p.pitch * (ROW_BYTES / 16));
     const int ndw_in = p.mode ? 2 : p.gemm ? 1 : ((p.ndw == 1) ? 3 : 1);   // dw taps served from one A box
@@ -284,30 +310,25 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       for (int j = 0; j < nblk; ++j) {
         mbar_wait(fullA + 8 * sa, pha);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        uint64_t adesc_dh = adesc_buf0 + (uint64_t)(sa * a_step + mu0 * (ROW_BYTES / 16));
+        uint32_t adesc_dh = a_lo0 + (uint32_t)(sa * a_step + mu0 * (ROW_BYTES / 16));
 #pragma unroll 1
         for (int dh = 0; dh < ndh_in; ++dh, adesc_dh += dh_step) {
-          uint64_t adesc = adesc_dh;
+          uint32_t adesc = adesc_dh;
           const uint32_t tcol = tacc + (uint32_t)dh * col_step;
           if (p.gemm) first = (j > 0) ? 1u : 0u;
 #pragma unroll 1
           for (int dw = 0; dw < ndw_in; ++dw, adesc += ROW_BYTES / 16) {
             mbar_wait(fullB + 8 * sb, phb);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint64_t bdesc = bdesc_buf0 + (uint64_t)(sb * b_step);
+            const uint32_t bdesc = b_lo0 + (uint32_t)(sb * b_step);
             if (elect_one()) {
 #pragma unroll
               for (int s = 0; s < MAXS; ++s) {
                 if (s < nsub) {
 #pragma unroll
-                  for (int k = 0; k < KCH / 8; ++k) {
-                    if (PAIR)
-                      umma_tf32_pair(tcol + (uint32_t)(s * N), adesc + (uint64_t)(s * (128 * ROW_BYTES / 16) + 2 * k),
-                                     bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
-                    else
-                      umma_tf32(tcol + (uint32_t)(s * N), adesc + (uint64_t)(s * (128 * ROW_BYTES / 16) + 2 * k),
-                                bdesc + (uint64_t)(2 * k), idesc, first | (uint32_t)k);
-                  }
+                  for (int k = 0; k < KCH / 8; ++k)
+                    umma_tf32_w<PAIR>(tcol + (uint32_t)(s * N), adesc + (uint32_t)(s * (128 * ROW_BYTES / 16) + 2 * k), a_hi,
+                                      bdesc + (uint32_t)(2 * k), b_hi, idesc, first | (uint32_t)k);
                 }
               }
               if (PAIR) umma_commit_pair(emptyB + 8 * sb);

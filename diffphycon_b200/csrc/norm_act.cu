@@ -275,6 +275,80 @@ extern "C" int dpc_layernorm_channels(const float* x, const float* gamma, const 
   return 0;
 }
 
+// final_conv[1] (conv3d.py:427, Conv3d(dim, out_dim, 1)) for out_dim <= 8, writing the reference layout [B,F,out_dim,H,W]:
+// HBM-bound (one read of the [M][C] activations); a warp stages its 32 consecutive rows through shared memory (coalesced
+// loads), each lane then owns one pixel: Cout dot products in fp32 against broadcast weights, Cout coalesced plane stores.
+template <int C, int COUT>
+__global__ void __launch_bounds__(128)
+final_proj_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                  float* __restrict__ out, int64_t M, int HW) {
+  constexpr int PITCH = C + 4;
+  __shared__ __align__(16) float s_w[COUT * C];
+  __shared__ __align__(16) float s_x[4][32 * PITCH];
+  for (int i = threadIdx.x; i < COUT * C; i += 128) s_w[i] = w[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* tile = s_x[warp];
+  float bv[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) bv[c] = bias ? bias[c] : 0.f;
+  const int64_t ngroups = (M + 31) / 32;
+  for (int64_t g = (int64_t)blockIdx.x * 4 + warp; g < ngroups; g += (int64_t)gridDim.x * 4) {
+    const int64_t r0 = g * 32;
+    const int nrows = (int)((M - r0) < 32 ? (M - r0) : 32);
+    const float4* src = reinterpret_cast<const float4*>(x + (size_t)r0 * C);
+#pragma unroll
+    for (int i = 0; i < C / 4; ++i) {                      // 32 rows x C floats = C/4 float4 per lane, lane-contiguous
+      const int idx = i * 32 + lane;                       // float4 index inside the 32-row slab
+      const int row = idx / (C / 4), col = idx - row * (C / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row < nrows) v = __ldcs(src + idx);
+      *reinterpret_cast<float4*>(tile + row * PITCH + col * 4) = v;
+    }
+    __syncwarp();
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = bv[c];
+#pragma unroll
+    for (int k = 0; k < C; k += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(tile + lane * PITCH + k);
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) {
+        const float4 ww = *reinterpret_cast<const float4*>(s_w + c * C + k);
+        acc[c] = fmaf(v.x, ww.x, acc[c]);
+        acc[c] = fmaf(v.y, ww.y, acc[c]);
+        acc[c] = fmaf(v.z, ww.z, acc[c]);
+        acc[c] = fmaf(v.w, ww.w, acc[c]);
+      }
+    }
+    __syncwarp();
+    const int64_t r = r0 + lane;
+    if (lane < nrows) {
+      const int64_t bf = r / HW;
+      const int pix = (int)(r - bf * HW);
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) __stcs(out + ((size_t)bf * COUT + c) * HW + pix, acc[c]);
+    }
+  }
+}
+
+extern "C" int dpc_final_proj(const float* x, const float* w, const float* bias, float* out, int64_t BF, int32_t HW, int32_t C,
+                              int32_t Cout, void* stream) {
+  using namespace dpc;
+  if (C != 64 || (Cout != 2 && Cout != 4 && Cout != 6)) return -2;   // other shapes: dpc_conv_igemm with out_layout = 1
+  DPC_CHECK_ARG(x && w && out && BF > 0 && HW > 0);
+  const int64_t M = BF * HW;
+  int64_t blocks = ((M + 31) / 32 + 3) / 4;
+  const int64_t cap = 148 * 6;
+  if (blocks > cap) blocks = cap;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Cout == 2) final_proj_kernel<64, 2><<<(unsigned)blocks, 128, 0, st>>>(x, w, bias, out, M, HW);
+  else if (Cout == 4) final_proj_kernel<64, 4><<<(unsigned)blocks, 128, 0, st>>>(x, w, bias, out, M, HW);
+  else final_proj_kernel<64, 6><<<(unsigned)blocks, 128, 0, st>>>(x, w, bias, out, M, HW);
+  DPC_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int dpc_pack_input(const float* x, float* out, int32_t B, int32_t F, int32_t Ctot, int32_t c0, int32_t Cin,
                               int32_t H, int32_t W, int32_t Cpad, void* stream) {
   using namespace dpc;

@@ -322,6 +322,7 @@ class Unet3D_with_Conv3D(nn.Module):
         pack_resnet("final_conv.0", self.final_conv[0])
         P["final_conv.1.w"] = packing.pack_linear(self.final_conv[1].weight.to(dev), tf32=rnd)
         P["final_conv.1.b"] = self.final_conv[1].bias.detach().float().to(dev).contiguous()
+        P["final_conv.1.wraw"] = self.final_conv[1].weight.detach().float().to(dev).reshape(self.out_dim, -1).contiguous()
 
         # time conditioning: one row-concatenated matrix for all ResnetBlock mlps (conv3d.py:211-214)
         ws, bs, offs, off = [], [], {}, 0
@@ -566,7 +567,7 @@ class Unet3D_with_Conv3D(nn.Module):
             if kind == "temporal":
                 _lib.temporal_attention(qkv, G["rope.cos"], G["rope.sin"], G["pos_bias"], att, B, F, h * w, heads, True, precise)
             elif kind == "spatial":
-                _lib.spatial_attention(qkv, att, B * F, h * w, heads)
+                _lib.spatial_attention(qkv, att, B * F, h * w, heads, precise=precise)
             else:
                 ctx = pool.get(B * F * heads * HEAD_DIM * HEAD_DIM)
                 _lib.spatial_linear_attention(qkv, ctx, att, B * F, h * w, heads)
@@ -670,7 +671,9 @@ class Unet3D_with_Conv3D(nn.Module):
         f0 = resnet("final_conv.0", cur, cur_c, 0, self.dim, xb=r, cb=d0, has_time=False)
         pool.put(cur)
         pool.put(r)
-        conv(f0, self.dim, P["final_conv.1.w"], P["final_conv.1.b"], out, self.out_dim, 0, "111", out_layout=1)
+        if not (out.is_contiguous() and _lib.final_proj(f0, P["final_conv.1.wraw"], P["final_conv.1.b"], out, B * F, H * W,
+                                                       self.dim, self.out_dim)):
+            conv(f0, self.dim, P["final_conv.1.w"], P["final_conv.1.b"], out, self.out_dim, 0, "111", out_layout=1)
         pool.put(f0)
         pool.put(ss)
         pool.put(stats)

@@ -109,6 +109,11 @@ int dpc_layernorm_channels(const float* x, const float* gamma, const float* resi
 /* nn.Upsample(scale_factor=2, mode='nearest') on channels-last [BF,H,W,C] -> [BF,2H,2W,C] (model/burgers_1d/unet.py:40-44). */
 int dpc_upsample_nearest2x(const float* x, float* out, int64_t BF, int32_t H, int32_t W, int32_t C, void* stream);
 
+/* final_conv[1] — conv3d.py:427, Conv3d(dim, out_dim, 1) — for dim == 64 and out_dim in {2, 4, 6}: x [BF*HW][64] channels-last
+ * -> out [BF][out_dim][HW] (the reference layout), w [out_dim][64] fp32, bias [out_dim] or NULL; fp32 FMAs.  Returns -2 for
+ * other shapes (served by dpc_conv_igemm with out_layout = 1). */
+int dpc_final_proj(const float* x, const float* w, const float* bias, float* out, int64_t BF, int32_t HW, int32_t C,
+                   int32_t Cout, void* stream);
 /* Reference layout [B,F,Ctot,H,W], channels [c0, c0+Cin) -> channels-last [B,F,H,W,Cpad] zero padded
  * (replaces the permute at conv3d.py:495 and the slice x[:, :, 3:5] at smoke.py:612). */
 int dpc_pack_input(const float* x, float* out, int32_t B, int32_t F, int32_t Ctot, int32_t c0, int32_t Cin,
@@ -139,6 +144,9 @@ int dpc_temporal_block_fused(const float* x, const float* w_qkv, const float* w_
 /* Softmax attention over the HW tokens of every frame (mid block) — conv3d.py:449-451 with Attention(:293-352),
  * no RoPE, no bias. */
 int dpc_spatial_attention(const float* qkv, float* out, int32_t BF, int32_t HW, int32_t heads, void* stream);
+/* Same attention with q k^T and P v on tensor cores (TF32 mma.sync, flash-attention style online softmax, fp32 accumulate);
+ * HW % 64 == 0, returns -2 otherwise. */
+int dpc_spatial_attention_mma(const float* qkv, float* out, int32_t BF, int32_t HW, int32_t heads, void* stream);
 /* Spatial linear attention — conv3d.py:243-257: q softmax over d, k softmax over pixels, v NOT divided by HW.
  * ctx_ws: workspace of BF*heads*32*32 floats. */
 int dpc_spatial_linear_attention(const float* qkv, float* ctx_ws, float* out, int32_t BF, int32_t HW, int32_t heads,

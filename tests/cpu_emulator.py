@@ -156,7 +156,7 @@ def temporal_block_fused(x, w_qkv, w_out, rope_cos, rope_sin, pos_bias, y, B, F,
     return True
 
 
-def spatial_attention(qkv, out, BF, HW, heads):
+def spatial_attention(qkv, out, BF, HW, heads, precise=True):
     hid = heads * HEADS_DIM
     t = qkv[: BF * HW * 3 * hid].reshape(BF, HW, 3 * hid)
     q, k, v = _split_heads(t, heads)
@@ -186,6 +186,16 @@ def stem_conv(x, w, bias, y, B, F, H, W, Cpad, N, kt, kh, kw):
     xin = x[: B * F * H * W * Cpad].reshape(B, F, H, W, Cpad).permute(0, 4, 1, 2, 3)
     o = torch.nn.functional.conv3d(xin.double(), wt.double(), bias.double(), padding=(kt // 2, kh // 2, 3))
     y[: B * F * H * W * N] = o.permute(0, 2, 3, 4, 1).float().reshape(-1)
+    return True
+
+
+def final_proj(x, w, bias, out, BF, HW, Cn, Cout):
+    if Cn != 64 or Cout not in (2, 4, 6):
+        return False
+    o = x[: BF * HW * Cn].reshape(BF, HW, Cn).double() @ w.double().t()
+    if bias is not None:
+        o = o + bias.double()
+    out.reshape(-1)[: BF * Cout * HW] = o.permute(0, 2, 1).float().reshape(-1)
     return True
 
 
@@ -334,7 +344,7 @@ def jelly_write_bd(pred_bd, bd_0, x_next, x_w, cond_steps):
     x_w[:, :, 3:6] = bd
 
 
-EMULATED = ("temporal_block_fused", "spatial_linear_block_fused", "stem_conv", "jelly_x_start", "jelly_step", "jelly_write_bd", "burgers_model_output", "ddpm_posterior_step", "conv", "groupnorm_silu", "layernorm_channels", "pack_input", "temporal_attention", "spatial_attention",
+EMULATED = ("temporal_block_fused", "final_proj", "spatial_linear_block_fused", "stem_conv", "jelly_x_start", "jelly_step", "jelly_write_bd", "burgers_model_output", "ddpm_posterior_step", "conv", "groupnorm_silu", "layernorm_channels", "pack_input", "temporal_attention", "spatial_attention",
             "spatial_linear_attention", "time_embed", "time_proj", "predict_x_start", "guided_step", "upsample_nearest2x")
 
 

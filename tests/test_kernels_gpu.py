@@ -141,6 +141,21 @@ def test_stem_conv_tcgen05_sliding_window(B, Fr, H, W, C, Cout):
     assert rel_err(y, ref) <= TOL_TF32
 
 
+@pytest.mark.parametrize("BF,HW,Cout,bias", [(3, 64, 6, True), (2, 4096, 2, True), (5, 100, 4, False), (1, 33, 6, True)])
+def test_final_proj_reference_layout(BF, HW, Cout, bias):
+    """dpc_final_proj (final_conv[1], conv3d.py:427) against fp64: fp32 FMAs, output in the reference layout [BF, Cout, HW]."""
+    gen = g(51)
+    x = torch.randn(BF * HW, 64, generator=gen)
+    w = torch.randn(Cout, 64, generator=gen) / 8
+    b = torch.randn(Cout, generator=gen) if bias else None
+    ref = x.double() @ w.double().t() + (b.double() if bias else 0)
+    ref = ref.reshape(BF, HW, Cout).permute(0, 2, 1)
+    out = torch.full((BF, Cout, HW), float("nan"), device=DEV)
+    assert _lib.final_proj(x.to(DEV), w.to(DEV), b.to(DEV) if bias else None, out, BF, HW, 64, Cout)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) <= TOL_F32
+
+
 def test_pack_input_slice():
     gen = g(3)
     x = torch.randn(2, 3, 6, 8, 12, generator=gen)
@@ -303,6 +318,20 @@ def test_spatial_attention(HW):
     ref = torch.empty(out.numel(), dtype=torch.float64)
     emu.spatial_attention(qkv.reshape(-1).double(), ref, BF, HW, heads)
     assert rel_err(out.reshape(-1), ref) <= TOL_F32
+
+
+@pytest.mark.parametrize("HW,scale", [(64, 1.5), (256, 1.5), (256, 4.0), (512, 1.0)])
+def test_spatial_attention_tensor_cores(HW, scale):
+    """dpc_spatial_attention_mma (TF32 mma.sync q k^T and P v, online softmax over 64-key blocks) against the fp64 emulator;
+    TF32 operand class.  scale 4 makes the softmax peaked (running-max rescaling matters); HW 512 = two query blocks."""
+    gen = g(11)
+    BF, heads = 3, 4
+    qkv = torch.randn(BF, HW, 384, generator=gen) * scale
+    out = torch.full((BF, HW, 128), float("nan"), device=DEV)
+    _lib.spatial_attention(qkv.to(DEV), out, BF, HW, heads, precise=False)
+    ref = torch.empty(out.numel(), dtype=torch.float64)
+    emu.spatial_attention(qkv.reshape(-1).double(), ref, BF, HW, heads)
+    assert rel_err(out.reshape(-1), ref) <= TOL_TF32 * (2 if scale > 2 else 1)
 
 
 @pytest.mark.parametrize("HW", [16, 100, 1024])
