@@ -48,6 +48,8 @@ struct Params {
                               // stride 2, 2x2 taps each); 2: one parity class of the 1x4x4 stride-2 ConvTranspose (2x2 taps)
   int cls_h, cls_w;           // mode 2: output parity class
   int Hout, Wout, o_mul;      // output frame and position scale: out(h, w) -> (h*o_mul + cls_h, w*o_mul + cls_w)
+  int quad;                   // PAIR + Cout = 64: a tile covers FOUR consecutive output frames; the three temporal taps that one
+                              // input frame feeds are stacked into one MMA of N = 64 / 128 / 192 (see the MMA issuer)
   int staged;                 // conv epilogue: stores staged through shared memory (128-byte row segments)
   int dbg;                    // DPC_TC_DEBUG experiment switches (1: weight boxes fetched once, 2: A boxes fetched once)
 };
@@ -67,6 +69,12 @@ __device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const CUtensorMap
   asm volatile(
       "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar_leader), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_leader, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar_leader), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar_leader, int c0, int c1) {
@@ -122,7 +130,7 @@ template <int N, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS_TC, 1)
 conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmA1t, const __grid_constant__ CUtensorMap tmA2t,
-                 const __grid_constant__ CUtensorMap tmW, const Params p) {
+                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmW3, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;           // 128B swizzle atoms need 1024-byte alignment
@@ -140,10 +148,12 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Cin = p.C1 + p.C2;
   const int nch = Cin / KCH, nch1 = p.C1 / KCH;
-  const int nblk = p.mode == 1 ? 4 * nch : p.mode == 2 ? nch : p.gemm ? nch : 3 * nch * p.ndw;   // A boxes per tile
+  const bool quad = PAIR && p.quad;
+  const int nblk = quad ? 6 * nch : p.mode == 1 ? 4 * nch : p.mode == 2 ? nch : p.gemm ? nch : 3 * nch * p.ndw;   // A boxes per tile
   const int ntap = p.mode ? 4 : p.gemm ? p.ncol : 9 / p.ndw;                                       // weight boxes per A box
   const int AB = p.AB;                                   // TMEM accumulator sets (2 = epilogue overlaps the next tile)
-  const int ntiles = p.B * p.F * p.tiles_f;
+  const int Fd = quad ? p.F / 4 : p.F;                  // frames (or frame quads) per sample in the tile enumeration
+  const int ntiles = p.B * Fd * p.tiles_f;
   // PAIR: the two CTAs of a cluster take the same spatial tile tf of two consecutive frames (same operand offsets in both
   // shared memories, which one shared A descriptor requires); iterations then count tile pairs.
   uint32_t cta_rank = 0;
@@ -183,6 +193,20 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+  if (quad) {
+    // quad mode always accumulates (an MMA spans accumulators in different states), so the accumulators start at zero
+    // and the epilogue re-zeroes what it has read
+    if (warp >= 4 && warp < 8) {
+      uint32_t z[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) z[j] = 0u;
+      for (int c = 0; c < 512; c += 32) tmem_st32(tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)c, z);
+      tmem_wait_st();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  }
 
   if (warp == 3 && lane == 0) {
     // ------------------------------------------- TMA producer: activations -------------------------------
@@ -196,13 +220,19 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     for (int a_it = it_begin; a_it < it_end; a_it += it_step) {
       const int a_tile = tile_of(a_it);
       const int tf = a_tile % p.tiles_f;
-      const int f = (a_tile / p.tiles_f) % p.F;
-      const int b = a_tile / (p.tiles_f * p.F);
+      int f = (a_tile / p.tiles_f) % Fd;
+      const int b = a_tile / (p.tiles_f * Fd);
       const int hq = (tf * p.S * 128) / p.pitch;
+      if (quad) f *= 4;                                      // first output frame of the quad
       for (int a_blk = 0; a_blk < nblk; ++a_blk, ++a_cnt) {
         int dt = 1, ch = a_blk, dwb = 1, halo = 0;           // gemm: centre tap only, no halo
         int w0 = 0, h0 = 0;
-        if (p.mode == 1) {                                   // parity box (ph, pw): input rows 2h + ph - 1 + 2*{0,1}, same in w
+        if (quad) {                                          // input frame f - 1 + (a_blk / nch): dt carries the frame offset
+          dt = a_blk / nch;
+          ch = a_blk - dt * nch;
+          dwb = 0;                                           // halo box: starts at column -1
+          halo = 1;
+        } else if (p.mode == 1) {                                   // parity box (ph, pw): input rows 2h + ph - 1 + 2*{0,1}, same in w
           const int par = a_blk / nch;
           ch = a_blk - par * nch;
           h0 = 2 * hq + ((par >> 1) ? -1 : 0);
@@ -253,6 +283,25 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           ch = rem / p.ndw;
           dwb = rem - ch * p.ndw;
         }
+        if (quad) {
+          // stacked weight rows R = dt*64 + n (a 3-D view of the packed weights): input frame index qi = j / nch feeds the
+          // output frames of the quad through rows [r0, r0 + n); each CTA of the pair holds half of them
+          const int qi = j / nch, qch = j - qi * nch;
+          const int r0 = qi <= 3 ? 0 : (qi - 3) * 64;
+          const int n = 64 * (qi < 3 ? qi + 1 : 6 - qi);
+          const int rmine = r0 + (int)cta_rank * (n / 2);
+          for (int t = 0; t < 9; ++t) {
+            mbar_wait(emptyB + 8 * sb, phb);
+            if (leader) mbar_expect_tx(fullB + 8 * sb, (uint32_t)(n * ROW_BYTES));
+            for (int q = 0; q < n / 64; ++q) {
+              const int row = rmine + 32 * q;
+              tma_load_3d_pair(b_buf + sb * p.b_bytes + q * (32 * ROW_BYTES), &tmW3, fullB_l + 8 * sb, t * Cin + qch * KCH, row & 63,
+                               row >> 6);
+            }
+            if (++sb == p.NB) { sb = 0; phb ^= 1; }
+          }
+          continue;
+        }
         // weight column of tap (dt, dh, dw): ((dt*3 + dh)*3 + dw)*Cin + ch*32; per box either all nine (dh,dw) or the three dh
         const int k0 = p.gemm ? ch * KCH : (dt * 9 + dwb) * Cin + ch * KCH;
         const int kstep = (p.ndw == 1) ? Cin : 3 * Cin;
@@ -293,7 +342,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     const int ndw_in = p.mode ? 2 : p.gemm ? 1 : ((p.ndw == 1) ? 3 : 1);   // dw taps served from one A box
     const int ndh_in = p.mode ? 2 : p.gemm ? p.ncol : 3;      // gemm: the "dh" loop walks the column tiles (A does not move)
     const uint32_t col_step = p.gemm ? (uint32_t)(p.S * N) : 0u;
-    const int ncolt = p.gemm ? p.ncol : 1;
+    const int ncolt = quad ? 4 : p.gemm ? p.ncol : 1;
+    const int acc_stride = quad ? 256 : N;               // TMEM columns between the accumulators of consecutive sub-tiles
     int sa = 0, sb = 0, ab = 0;
     uint32_t pha = 0, phb = 0, phacc = 1;
     for (int it = it_begin; it < it_end; it += it_step) {
@@ -308,13 +358,22 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       const uint32_t tacc = tmem_base + (uint32_t)(ab * p.S * N * ncolt);
       uint32_t first = 0;
       for (int j = 0; j < nblk; ++j) {
+        // quad: accumulators of output frames f0..f0+3 sit at columns 192, 128, 64, 0 of each 256-column sub-tile set (rows of
+        // the stacked weights run dt = 0, 1, 2, i.e. towards EARLIER output frames); input frame index qi spans n columns
+        uint32_t idesc_j = idesc, qcol = 0;
+        if (quad) {
+          const int qi = j / nch;
+          const int n = 64 * (qi < 3 ? qi + 1 : 6 - qi);
+          qcol = qi <= 2 ? (uint32_t)(192 - 64 * qi) : 0u;
+          idesc_j = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(n >> 3) << 17);
+        }
         mbar_wait(fullA + 8 * sa, pha);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t adesc_dh = a_lo0 + (uint32_t)(sa * a_step + mu0 * (ROW_BYTES / 16));
 #pragma unroll 1
         for (int dh = 0; dh < ndh_in; ++dh, adesc_dh += dh_step) {
           uint32_t adesc = adesc_dh;
-          const uint32_t tcol = tacc + (uint32_t)dh * col_step;
+          const uint32_t tcol = tacc + (uint32_t)dh * col_step + qcol;
           if (p.gemm) first = (j > 0) ? 1u : 0u;
 #pragma unroll 1
           for (int dw = 0; dw < ndw_in; ++dw, adesc += ROW_BYTES / 16) {
@@ -327,8 +386,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
                 if (s < nsub) {
 #pragma unroll
                   for (int k = 0; k < KCH / 8; ++k)
-                    umma_tf32_w<PAIR>(tcol + (uint32_t)(s * N), adesc + (uint32_t)(s * (128 * ROW_BYTES / 16) + 2 * k), a_hi,
-                                      bdesc + (uint32_t)(2 * k), b_hi, idesc, first | (uint32_t)k);
+                    umma_tf32_w<PAIR>(tcol + (uint32_t)(s * acc_stride), adesc + (uint32_t)(s * (128 * ROW_BYTES / 16) + 2 * k), a_hi,
+                                      bdesc + (uint32_t)(2 * k), b_hi, idesc_j, quad ? 1u : (first | (uint32_t)k));
                 }
               }
               if (PAIR) umma_commit_pair(emptyB + 8 * sb);
@@ -361,8 +420,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     for (int it = it_begin; it < it_end; it += it_step) {
       const int tile = tile_of(it);
       const int tf = tile % p.tiles_f;
-      const int f = (tile / p.tiles_f) % p.F;
-      const int b = tile / (p.tiles_f * p.F);
+      const int f = ((tile / p.tiles_f) % Fd) * (quad ? 4 : 1);   // quad: first output frame of the tile
+      const int b = tile / (p.tiles_f * Fd);
       const int mu_tile = tf * p.S * 128;
       const int npos = p.H * p.pitch - mu_tile;
       const int nsub = (npos >= p.S * 128) ? p.S : (npos + 127) / 128;
@@ -371,7 +430,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       for (int g = 0; g < 8; ++g) fs[g] = fq[g] = 0.f;
       mbar_wait(acc_full + 8 * ab, phacc);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.S * N * (p.gemm ? p.ncol : 1));
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.S * N * (quad ? 4 : p.gemm ? p.ncol : 1));
       if (p.gemm) {
         // Linear / 1x1x1 epilogue: the tile is store-bound, so rows are staged through a per-warp shared-memory tile
         // (32 rows x 36 floats, conflict-free float4 both ways) and written as 128-byte row segments: a warp store
@@ -434,9 +493,13 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           __syncwarp();
         }
       } else
-      for (int s = eg; s < nsub; s += 2) {
+      for (int item = eg; item < (quad ? 4 * nsub : nsub); item += 2) {
+        // quad: item = (sub-tile, frame of the quad); its accumulator sits at columns s*256 + (3 - i)*64
+        const int s = quad ? item >> 2 : item;
+        const int qfr = quad ? item & 3 : 0;
+        const uint32_t acol = quad ? (uint32_t)(s * 256 + (3 - qfr) * 64) : (uint32_t)(s * N);
         const int mu_w = mu_tile + s * 128 + q * 32;        // first padded-flat position of this warp's 32 rows
-        const size_t bf = (size_t)b * p.F + f;
+        const size_t bf = (size_t)b * p.F + f + qfr;
         auto out_row = [&](int mu, bool& ok) -> size_t {     // output row index of position mu
           const int h = mu / p.pitch, w = mu - h * p.pitch;
           ok = (h < p.H) && (w < p.W);
@@ -465,7 +528,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
 #pragma unroll
         for (int c = 0; c < N / 32; ++c) {
           uint32_t v[32];
-          tmem_ld32(tacc + (uint32_t)(s * N + c * 32), v);
+          tmem_ld32(tacc + acol + (uint32_t)(c * 32), v);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           float o[32];
 #pragma unroll
@@ -476,6 +539,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             o[j + 1] = __uint_as_float(v[j + 1]) + bv.y;
             o[j + 2] = __uint_as_float(v[j + 2]) + bv.z;
             o[j + 3] = __uint_as_float(v[j + 3]) + bv.w;
+          }
+          if (quad) {                                      // leave the accumulator at zero for the next tile
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0u;
+            tmem_st32(tacc + acol + (uint32_t)(c * 32), v);
           }
           if (p.staged) {
 #pragma unroll
@@ -509,6 +577,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         }
       }
       // accumulator set drained: hand it back to the MMA warp before the (slower) statistics reduction
+      if (quad) tmem_wait_st();
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) {
@@ -585,14 +654,14 @@ static int make_w_map(CUtensorMap* m, const float* w, int Kpad, int Npad, int N)
 
 template <int N, bool PAIR>
 static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& a1t, const CUtensorMap& a2t,
-                  const CUtensorMap& wm, const Params& p, size_t smem, cudaStream_t st) {
+                  const CUtensorMap& wm, const CUtensorMap& wm3, const Params& p, size_t smem, cudaStream_t st) {
   static size_t configured = 0;
   if (smem > configured) {
     DPC_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<N, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (PAIR) DPC_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<N, PAIR>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
     configured = smem;
   }
-  const size_t ntiles = (size_t)p.B * p.F * p.tiles_f;
+  const size_t ntiles = (size_t)p.B * (p.quad ? p.F / 4 : p.F) * p.tiles_f;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
@@ -628,7 +697,7 @@ static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMa
   } else {
     cfg.gridDim = dim3((unsigned)(ntiles < (size_t)num_sms ? ntiles : (size_t)num_sms));   // persistent: one CTA per SM
   }
-  DPC_CUDA(cudaLaunchKernelEx(&cfg, conv3d_tc_kernel<N, PAIR>, a1, a2, a1t, a2t, wm, p));
+  DPC_CUDA(cudaLaunchKernelEx(&cfg, conv3d_tc_kernel<N, PAIR>, a1, a2, a1t, a2t, wm, wm3, p));
   DPC_LAUNCH_CHECK();
   return 0;
 }
@@ -684,11 +753,19 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   p.ndw = (mode || (!gemm && W >= 32)) ? 1 : 3;
   p.pitch = mode ? p.W + 1 : (p.ndw == 1) ? W + 2 : W;   // 2x2 taps: one halo column
   const int frame_pos = p.H * p.pitch;
+  // quad (Cout = 64, large frames): four output frames per tile, temporal taps stacked into N = 64/128/192 MMAs; needs whole
+  // quads per sample and an even number of quads for the CTA pairs.  Measured neutral (64->64 @64^2: 2.78 vs 2.85 ms,
+  // 128->64: 5.6 vs 6.1 ms, 32^2 layers slightly slower: single-buffered accumulators, per-column MMA cost does not drop
+  // with N), so it is opt-in: DPC_TC_QUAD=1.
+  const char* quad_env = getenv("DPC_TC_QUAD");
+  const bool quad = pair && c.Cout == 64 && p.ndw == 1 && F % 4 == 0 && ((int64_t)c.B * (F / 4)) % 2 == 0 &&
+                    quad_env && atoi(quad_env) == 1;
+  p.quad = quad ? 1 : 0;
   // gemm: up to 512 accumulator columns = ncol column tiles side by side, so A is read once for (up to) 512 outputs
   int ncol = 1;
   if (gemm) { ncol = c.Cout / Ntile; if (ncol * Ntile > 512) ncol = 512 / Ntile; }
   p.ncol = ncol;
-  int S = gemm ? 256 / (ncol * Ntile) : 512 / Ntile;   // gemm tiles are store-bound: keep two accumulator sets when they fit
+  int S = gemm ? 256 / (ncol * Ntile) : quad ? 2 : 512 / Ntile;   // gemm tiles are store-bound: keep two accumulator sets when they fit
   if (S < 1) S = 1;
   if (S > MAXS) S = MAXS;
   if (S > (frame_pos + 127) / 128) S = (frame_pos + 127) / 128;
@@ -696,7 +773,7 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   const size_t stage_full = (size_t)8 * 32 * 36 * sizeof(float);
   size_t stage_bytes = gemm ? stage_full : 0;
   int NA = 2;
-  p.b_bytes = (pair ? Ntile / 2 : Ntile) * ROW_BYTES;    // a pair splits every weight box between its two CTAs
+  p.b_bytes = (quad ? 96 : pair ? Ntile / 2 : Ntile) * ROW_BYTES;    // a pair splits every weight box between its two CTAs
   for (;; --S) {
     // rows needed: offset inside the first row (< pitch) + S*128 positions (+ two more image rows + 2 positions of halo)
     const int span = p.pitch - 1 + S * 128 + (gemm ? 0 : mode ? p.pitch + 1 : 2 * p.pitch + 2);
@@ -728,8 +805,8 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   if (!gemm && (size_t)3 * p.a_bytes + 4 * (size_t)p.b_bytes + 1024 + 256 + stage_bytes <= budget) NA = 3;
   p.NA = NA;
   p.S = S;
-  p.AB = (2 * S * ncol * Ntile <= 512) ? 2 : 1;
-  { int need = p.AB * S * ncol * Ntile; p.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512; }
+  p.AB = (!quad && 2 * S * ncol * Ntile <= 512) ? 2 : 1;
+  { int need = quad ? 512 : p.AB * S * ncol * Ntile; p.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512; }
   p.tiles_f = (frame_pos + S * 128 - 1) / (S * 128);
   int NB = (int)((budget - 1024 - 256 - stage_bytes - (size_t)NA * p.a_bytes) / p.b_bytes);
   if (NB > 9) NB = 9;
@@ -757,18 +834,31 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   }
   rc = make_w_map(&wm, c.w, c.Kpad, c.Npad, pair ? Ntile / 2 : Ntile);
   if (rc) return rc;
+  CUtensorMap wm3 = wm;
+  if (quad) {
+    // 3-D view of the packed weights [64][27*Cin]: (k' = (dh*3+dw)*Cin + ci, n, dt), boxes of 32 rows of one dt
+    EncodeTiledFn enc = get_encode();
+    const int Cin = c.C1 + c.C2;
+    cuuint64_t dims[3] = {(cuuint64_t)(9 * Cin), 64, 3};
+    cuuint64_t strides[2] = {(cuuint64_t)c.Kpad * 4, (cuuint64_t)(9 * Cin) * 4};
+    cuuint32_t box[3] = {(cuuint32_t)KCH, 32, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&wm3, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)c.w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_err(-1, "cuTensorMapEncodeTiled(stacked weights) failed", __FILE__, (int)r);
+  }
   cudaStream_t st = (cudaStream_t)stream;
   for (int n0 = 0; n0 < c.Cout; n0 += ncol * Ntile) {
     if (gemm && c.Cout - n0 < ncol * Ntile) p.ncol = (c.Cout - n0) / Ntile;
     p.wrow0 = n0;
     p.bias = c.bias ? c.bias + n0 : nullptr;
     if (pair) {
-      if (Ntile == 64) rc = launch<64, true>(a1, a2, a1t, a2t, wm, p, smem, st);
-      else if (Ntile == 128) rc = launch<128, true>(a1, a2, a1t, a2t, wm, p, smem, st);
-      else rc = launch<256, true>(a1, a2, a1t, a2t, wm, p, smem, st);
-    } else if (Ntile == 64) rc = launch<64, false>(a1, a2, a1t, a2t, wm, p, smem, st);
-    else if (Ntile == 128) rc = launch<128, false>(a1, a2, a1t, a2t, wm, p, smem, st);
-    else rc = launch<256, false>(a1, a2, a1t, a2t, wm, p, smem, st);
+      if (Ntile == 64) rc = launch<64, true>(a1, a2, a1t, a2t, wm, wm3, p, smem, st);
+      else if (Ntile == 128) rc = launch<128, true>(a1, a2, a1t, a2t, wm, wm3, p, smem, st);
+      else rc = launch<256, true>(a1, a2, a1t, a2t, wm, wm3, p, smem, st);
+    } else if (Ntile == 64) rc = launch<64, false>(a1, a2, a1t, a2t, wm, wm3, p, smem, st);
+    else if (Ntile == 128) rc = launch<128, false>(a1, a2, a1t, a2t, wm, wm3, p, smem, st);
+    else rc = launch<256, false>(a1, a2, a1t, a2t, wm, wm3, p, smem, st);
     if (rc) return rc;
   }
   return 0;

@@ -438,16 +438,23 @@ TC_CASES = [
     ("w8_128", 2, 4, 8, 8, 128, 0, 128),
     ("w4_256", 1, 6, 4, 4, 256, 0, 256),
     ("nonsquare_h12_w20", 2, 3, 12, 20, 64, 0, 64),
+    # quad mode (Cout = 64, W >= 32, whole frame quads, even number of quads): stacked temporal taps, N = 64/128/192 MMAs
+    ("quad_w32_64", 1, 8, 32, 32, 64, 0, 64),
+    ("quad_w64_concat_128_to_64", 2, 4, 64, 64, 64, 64, 64),
+    ("quad_h40_w36_ragged", 1, 8, 40, 36, 64, 0, 64),
+    ("quad_f16_w32_256_to_64", 1, 16, 8, 32, 256, 0, 64),
 ]
 
 
-@pytest.mark.parametrize("pair", [True, False], ids=["cta_pair", "single_cta"])
+@pytest.mark.parametrize("pair", [True, False, "quad"], ids=["cta_pair", "single_cta", "cta_pair_quad"])
 @pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
 def test_conv3d_tcgen05(case, pair, monkeypatch):
     """The TMA/tcgen05 kernel against fp64 conv3d and against the generic tensor-core kernel (same numerics class).
-    cta_pair: cta_group::2 clusters (the default when B*F is even); single_cta: DPC_TC_PAIR=0 forces one CTA per tile."""
+    cta_pair: cta_group::2 clusters (the default when B*F is even); single_cta: DPC_TC_PAIR=0 forces one CTA per tile;
+    cta_pair_quad: DPC_TC_QUAD=1, four output frames per tile with the temporal taps stacked into N = 64/128/192 MMAs."""
     _, B, Fr, H, W, C1, C2, Cout = case
     monkeypatch.setenv("DPC_TC_PAIR", "1" if pair else "0")
+    monkeypatch.setenv("DPC_TC_QUAD", "1" if pair == "quad" else "0")   # opt-in stacked-temporal-tap mode (Cout = 64 shapes)
     gen = g(21)
     x1 = torch.randn(B, Fr, H, W, C1, generator=gen)
     x2 = torch.randn(B, Fr, H, W, C2, generator=gen) if C2 else None
