@@ -9,7 +9,8 @@
 // sliding window of the convolution, no im2col copy (layout verified on B200 with tools/umma_noswizzle_probe.cu).
 // Outputs are enumerated in padded-flat order mu = h * PW + w' (PW = W + 6; columns w' >= W are computed and discarded), so tap (dh, dw) of a 128-row operand is the same buffer shifted by dh * PW + dw pixels.
 // Weights stream through a TMA ring as 128B-swizzled [N][32] boxes; S = 4 accumulators of 128 x N share each weight box.
-// Warp roles as conv3d_tcgen05.cu: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 epilogue.
+// Warp roles as conv3d_tcgen05.cu: warp 0 weight TMA producer, warp 3 input TMA producer, warp 1 MMA issuer, warp 2 TMEM
+// allocator, warps 4-11 epilogue.
 #include "tc_common.cuh"
 
 namespace dpc {
@@ -77,28 +78,30 @@ stem_conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint32_t tmem_base;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
-  if (warp == 0 && lane == 0) {
-    // ------------------------------------------- TMA producer -------------------------------------------
-    int sa = 0, sb = 0;
-    uint32_t pha = 1, phb = 1;
-    int a_tile = blockIdx.x, a_blk = 0;                   // the A stream runs one block ahead of the weight stream
-    auto issue_a = [&]() {
-      if (a_tile >= ntiles) return;
+  if (warp == 3 && lane == 0) {
+    // ------------------------------------------- TMA producer: input rows ------------------------------
+    // (own thread: the weight stream below blocks on its own ring)
+    int sa = 0;
+    uint32_t pha = 1;
+    for (int a_tile = blockIdx.x; a_tile < ntiles; a_tile += gridDim.x) {
       const int tf = a_tile % p.tiles_f;
       const int f = (a_tile / p.tiles_f) % p.F;
       const int b = a_tile / (p.tiles_f * p.F);
       const int hq = (tf * p.S * 128) / p.PW;
-      const int dt = a_blk / p.P, pl = a_blk - dt * p.P;
-      mbar_wait(emptyA + 8 * sa, pha);
-      mbar_expect_tx(fullA + 8 * sa, (uint32_t)p.a_tx);
-      tma_load_5d(a_buf + sa * p.a_bytes, &tmA, fullA + 8 * sa, pl * 4, -3, hq - p.ph, f + dt - p.pt, b);
-      if (++sa == NA) { sa = 0; pha ^= 1; }
-      if (++a_blk == nblk) { a_blk = 0; a_tile += gridDim.x; }
-    };
-    issue_a();
+      for (int a_blk = 0; a_blk < nblk; ++a_blk) {
+        const int dt = a_blk / p.P, pl = a_blk - dt * p.P;
+        mbar_wait(emptyA + 8 * sa, pha);
+        mbar_expect_tx(fullA + 8 * sa, (uint32_t)p.a_tx);
+        tma_load_5d(a_buf + sa * p.a_bytes, &tmA, fullA + 8 * sa, pl * 4, -3, hq - p.ph, f + dt - p.pt, b);
+        if (++sa == NA) { sa = 0; pha ^= 1; }
+      }
+    }
+  } else if (warp == 0 && lane == 0) {
+    // ------------------------------------------- TMA producer: weights ---------------------------------
+    int sb = 0;
+    uint32_t phb = 1;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       for (int j = 0; j < nblk; ++j) {
-        issue_a();                                        // box of the next block
         const int dt = j / p.P, pl = j - dt * p.P;
         for (int dh = 0; dh < p.kh; ++dh) {
           mbar_wait(emptyB + 8 * sb, phb);
