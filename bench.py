@@ -305,7 +305,7 @@ def main():
             traffic = None
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["tensor_burst"], "unit": "TFLOP/s",
                 "frac": ach / pk["tensor_burst"], "frac_of_tf32_roof": ach / (pk["tensor_burst"] / 2), "traffic": traffic,
-                "traffic_note": "bytes per launch (ncu, profiles/r1_ncu_full_v7.txt); algorithmic = %d" % (2 * Bc * FRAMES * SIZE * SIZE * 64 * 4),
+                "traffic_note": "bytes per launch (ncu, profiles/r1_ncu_full_v12.txt); algorithmic = %d" % (2 * Bc * FRAMES * SIZE * SIZE * 64 * 4),
                 "kernel": "conv3d_tcgen05 3x3x3 64->64" if used_tc else "conv_igemm (mma.sync) 3x3x3 64->64",
                 "kernel_ms": kms, "kernel_batch": Bc, "peak_source": pk["source"] + " bf16 burst (kernel timed alone); TF32 nominal peak is half of bf16",
                 "step_tensor_tflops": FLOPS_PER_SAMPLE_STEP * B / (ms_per_step / 1e3) / 1e12,
