@@ -109,3 +109,28 @@ def test_metric_shape_forward_properties():
     y_generic = net(x, t)
     scale = y_generic.abs().max().item()
     assert (y - y_generic).abs().max().item() <= 2e-3 * max(1.0, scale)
+
+
+@pytest.mark.parametrize("frames,size,channels,out_dim", [(64, 128, 6, None), (20, 128, 7, 4), (5, 64, 6, None), (32, 32, 2, None)])
+def test_other_config_shapes_forward_properties(frames, size, channels, out_dim):
+    """The other BASELINE.json configurations' shapes at batch 1 (128x128 with 64 frames = config 5, the jellyfish 20-frame
+    128x128 network = config 3) plus an odd frame count (no CTA pairs) and a small frame: finite, deterministic, and the tcgen05
+    path (pairs, fused blocks where their shape gates admit them, stem / down / transposed kernels) equals the generic
+    tensor-core path within TF32 accumulation-order noise."""
+    kw = dict(dim=64, dim_mults=(1, 2, 4), channels=channels)
+    if out_dim is not None:
+        kw["out_dim"] = out_dim
+    cfg = uo.UnetCfg(**kw)
+    net = dpc.Unet3D_with_Conv3D(**kw)
+    net.load_state_dict(uo.make_params(cfg, 41))
+    net = net.cuda()
+    g = torch.Generator().manual_seed(42)
+    x = torch.randn(1, frames, channels, size, size, generator=g).cuda()
+    t = torch.tensor([654]).cuda()
+    y = net(x, t)
+    assert y.shape == (1, frames, out_dim or channels, size, size) and torch.isfinite(y).all()
+    assert torch.equal(y, net(x, t))
+    net.use_tcgen05 = False
+    y_generic = net(x, t)
+    scale = y_generic.abs().max().item()
+    assert (y - y_generic).abs().max().item() <= 2e-3 * max(1.0, scale)
