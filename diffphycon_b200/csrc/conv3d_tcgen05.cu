@@ -48,7 +48,7 @@ struct Params {
                               // stride 2, 2x2 taps each); 2: one parity class of the 1x4x4 stride-2 ConvTranspose (2x2 taps)
   int cls_h, cls_w;           // mode 2: output parity class
   int Hout, Wout, o_mul;      // output frame and position scale: out(h, w) -> (h*o_mul + cls_h, w*o_mul + cls_w)
-  int quad;                   // PAIR + Cout = 64: a tile covers FOUR consecutive output frames; the three temporal taps that one
+  int quad;                   // PAIR + Cout = 64: Q = 2 or 4 (0 = off); a tile covers Q consecutive output frames; the temporal taps that one
                               // input frame feeds are stacked into one MMA of N = 64 / 128 / 192 (see the MMA issuer)
   int staged;                 // conv epilogue: stores staged through shared memory (128-byte row segments)
   int dbg;                    // DPC_TC_DEBUG experiment switches (1: weight boxes fetched once, 2: A boxes fetched once)
@@ -149,10 +149,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   const int Cin = p.C1 + p.C2;
   const int nch = Cin / KCH, nch1 = p.C1 / KCH;
   const bool quad = PAIR && p.quad;
-  const int nblk = quad ? 6 * nch : p.mode == 1 ? 4 * nch : p.mode == 2 ? nch : p.gemm ? nch : 3 * nch * p.ndw;   // A boxes per tile
+  const int Q = quad ? p.quad : 1;                      // output frames per tile
+  const int nblk = quad ? (Q + 2) * nch : p.mode == 1 ? 4 * nch : p.mode == 2 ? nch : p.gemm ? nch : 3 * nch * p.ndw;   // A boxes per tile
   const int ntap = p.mode ? 4 : p.gemm ? p.ncol : 9 / p.ndw;                                       // weight boxes per A box
   const int AB = p.AB;                                   // TMEM accumulator sets (2 = epilogue overlaps the next tile)
-  const int Fd = quad ? p.F / 4 : p.F;                  // frames (or frame quads) per sample in the tile enumeration
+  const int Fd = quad ? p.F / Q : p.F;                  // frames (or frame quads) per sample in the tile enumeration
   const int ntiles = p.B * Fd * p.tiles_f;
   // PAIR: the two CTAs of a cluster take the same spatial tile tf of two consecutive frames (same operand offsets in both
   // shared memories, which one shared A descriptor requires); iterations then count tile pairs.
@@ -223,7 +224,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       int f = (a_tile / p.tiles_f) % Fd;
       const int b = a_tile / (p.tiles_f * Fd);
       const int hq = (tf * p.S * 128) / p.pitch;
-      if (quad) f *= 4;                                      // first output frame of the quad
+      if (quad) f *= Q;                                      // first output frame of the tile
       for (int a_blk = 0; a_blk < nblk; ++a_blk, ++a_cnt) {
         int dt = 1, ch = a_blk, dwb = 1, halo = 0;           // gemm: centre tap only, no halo
         int w0 = 0, h0 = 0;
@@ -287,8 +288,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           // stacked weight rows R = dt*64 + n (a 3-D view of the packed weights): input frame index qi = j / nch feeds the
           // output frames of the quad through rows [r0, r0 + n); each CTA of the pair holds half of them
           const int qi = j / nch, qch = j - qi * nch;
-          const int r0 = qi <= 3 ? 0 : (qi - 3) * 64;
-          const int n = 64 * (qi < 3 ? qi + 1 : 6 - qi);
+          const int dt_lo = qi - Q + 1 > 0 ? qi - Q + 1 : 0, dt_hi = qi < 2 ? qi : 2;   // output frame i = qi - dt in [0, Q)
+          const int r0 = dt_lo * 64;
+          const int n = 64 * (dt_hi - dt_lo + 1);
           const int rmine = r0 + (int)cta_rank * (n / 2);
           for (int t = 0; t < 9; ++t) {
             mbar_wait(emptyB + 8 * sb, phb);
@@ -342,8 +344,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     const int ndw_in = p.mode ? 2 : p.gemm ? 1 : ((p.ndw == 1) ? 3 : 1);   // dw taps served from one A box
     const int ndh_in = p.mode ? 2 : p.gemm ? p.ncol : 3;      // gemm: the "dh" loop walks the column tiles (A does not move)
     const uint32_t col_step = p.gemm ? (uint32_t)(p.S * N) : 0u;
-    const int ncolt = quad ? 4 : p.gemm ? p.ncol : 1;
-    const int acc_stride = quad ? 256 : N;               // TMEM columns between the accumulators of consecutive sub-tiles
+    const int ncolt = quad ? Q : p.gemm ? p.ncol : 1;
+    const int acc_stride = quad ? Q * 64 : N;               // TMEM columns between the accumulators of consecutive sub-tiles
     int sa = 0, sb = 0, ab = 0;
     uint32_t pha = 0, phb = 0, phacc = 1;
     for (int it = it_begin; it < it_end; it += it_step) {
@@ -363,8 +365,9 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
         uint32_t idesc_j = idesc, qcol = 0;
         if (quad) {
           const int qi = j / nch;
-          const int n = 64 * (qi < 3 ? qi + 1 : 6 - qi);
-          qcol = qi <= 2 ? (uint32_t)(192 - 64 * qi) : 0u;
+          const int dt_lo = qi - Q + 1 > 0 ? qi - Q + 1 : 0, dt_hi = qi < 2 ? qi : 2;
+          const int n = 64 * (dt_hi - dt_lo + 1);
+          qcol = (uint32_t)((Q - 1 - qi + dt_lo) * 64);      // accumulator of output frame i sits at column (Q-1-i)*64
           idesc_j = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(n >> 3) << 17);
         }
         mbar_wait(fullA + 8 * sa, pha);
@@ -420,7 +423,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
     for (int it = it_begin; it < it_end; it += it_step) {
       const int tile = tile_of(it);
       const int tf = tile % p.tiles_f;
-      const int f = ((tile / p.tiles_f) % Fd) * (quad ? 4 : 1);   // quad: first output frame of the tile
+      const int f = ((tile / p.tiles_f) % Fd) * Q;   // quad: first output frame of the tile
       const int b = tile / (p.tiles_f * Fd);
       const int mu_tile = tf * p.S * 128;
       const int npos = p.H * p.pitch - mu_tile;
@@ -430,7 +433,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
       for (int g = 0; g < 8; ++g) fs[g] = fq[g] = 0.f;
       mbar_wait(acc_full + 8 * ab, phacc);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.S * N * (quad ? 4 : p.gemm ? p.ncol : 1));
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ab * p.S * N * (quad ? Q : p.gemm ? p.ncol : 1));
       if (p.gemm) {
         // Linear / 1x1x1 epilogue: the tile is store-bound, so rows are staged through a per-warp shared-memory tile
         // (32 rows x 36 floats, conflict-free float4 both ways) and written as 128-byte row segments: a warp store
@@ -493,11 +496,11 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           __syncwarp();
         }
       } else
-      for (int item = eg; item < (quad ? 4 * nsub : nsub); item += 2) {
-        // quad: item = (sub-tile, frame of the quad); its accumulator sits at columns s*256 + (3 - i)*64
-        const int s = quad ? item >> 2 : item;
-        const int qfr = quad ? item & 3 : 0;
-        const uint32_t acol = quad ? (uint32_t)(s * 256 + (3 - qfr) * 64) : (uint32_t)(s * N);
+      for (int item = eg; item < Q * nsub; item += 2) {
+        // quad: item = (sub-tile, frame of the tile); its accumulator sits at columns (s*Q + Q-1-i)*64
+        const int s = item / Q;
+        const int qfr = item - s * Q;
+        const uint32_t acol = quad ? (uint32_t)((s * Q + Q - 1 - qfr) * 64) : (uint32_t)(s * N);
         const int mu_w = mu_tile + s * 128 + q * 32;        // first padded-flat position of this warp's 32 rows
         const size_t bf = (size_t)b * p.F + f + qfr;
         auto out_row = [&](int mu, bool& ok) -> size_t {     // output row index of position mu
@@ -661,7 +664,7 @@ static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMa
     if (PAIR) DPC_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<N, PAIR>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
     configured = smem;
   }
-  const size_t ntiles = (size_t)p.B * (p.quad ? p.F / 4 : p.F) * p.tiles_f;
+  const size_t ntiles = (size_t)p.B * (p.quad ? p.F / p.quad : p.F) * p.tiles_f;
   static int num_sms = 0;
   if (!num_sms) {
     int dev = 0;
@@ -758,9 +761,11 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   // 128->64: 5.6 vs 6.1 ms, 32^2 layers slightly slower: single-buffered accumulators, per-column MMA cost does not drop
   // with N), so it is opt-in: DPC_TC_QUAD=1.
   const char* quad_env = getenv("DPC_TC_QUAD");
-  const bool quad = pair && c.Cout == 64 && p.ndw == 1 && F % 4 == 0 && ((int64_t)c.B * (F / 4)) % 2 == 0 &&
-                    quad_env && atoi(quad_env) == 1;
-  p.quad = quad ? 1 : 0;
+  const int Qreq = quad_env ? atoi(quad_env) : 0;      // 1 or 4: four frames per tile; 2: two frames per tile
+  const int Qn = Qreq == 2 ? 2 : 4;
+  const bool quad = pair && c.Cout == 64 && p.ndw == 1 && F % Qn == 0 && ((int64_t)c.B * (F / Qn)) % 2 == 0 &&
+                    (Qreq == 1 || Qreq == 2 || Qreq == 4);
+  p.quad = quad ? Qn : 0;
   // gemm: up to 512 accumulator columns = ncol column tiles side by side, so A is read once for (up to) 512 outputs
   int ncol = 1;
   if (gemm) { ncol = c.Cout / Ntile; if (ncol * Ntile > 512) ncol = 512 / Ntile; }
@@ -773,7 +778,7 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   const size_t stage_full = (size_t)8 * 32 * 36 * sizeof(float);
   size_t stage_bytes = gemm ? stage_full : 0;
   int NA = 2;
-  p.b_bytes = (quad ? 96 : pair ? Ntile / 2 : Ntile) * ROW_BYTES;    // a pair splits every weight box between its two CTAs
+  p.b_bytes = (quad ? (Qn == 2 ? 64 : 96) : pair ? Ntile / 2 : Ntile) * ROW_BYTES;    // a pair splits every weight box between its two CTAs
   for (;; --S) {
     // rows needed: offset inside the first row (< pitch) + S*128 positions (+ two more image rows + 2 positions of halo)
     const int span = p.pitch - 1 + S * 128 + (gemm ? 0 : mode ? p.pitch + 1 : 2 * p.pitch + 2);
@@ -805,7 +810,7 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   if (!gemm && (size_t)3 * p.a_bytes + 4 * (size_t)p.b_bytes + 1024 + 256 + stage_bytes <= budget) NA = 3;
   p.NA = NA;
   p.S = S;
-  p.AB = (!quad && 2 * S * ncol * Ntile <= 512) ? 2 : 1;
+  p.AB = quad ? (2 * S * Qn * 64 <= 512 ? 2 : 1) : (2 * S * ncol * Ntile <= 512) ? 2 : 1;
   { int need = quad ? 512 : p.AB * S * ncol * Ntile; p.tmem_cols = need <= 32 ? 32 : need <= 64 ? 64 : need <= 128 ? 128 : need <= 256 ? 256 : 512; }
   p.tiles_f = (frame_pos + S * 128 - 1) / (S * 128);
   int NB = (int)((budget - 1024 - 256 - stage_bytes - (size_t)NA * p.a_bytes) / p.b_bytes);

@@ -446,7 +446,7 @@ TC_CASES = [
 ]
 
 
-@pytest.mark.parametrize("pair", [True, False, "quad"], ids=["cta_pair", "single_cta", "cta_pair_quad"])
+@pytest.mark.parametrize("pair", [True, False, "quad", "duo"], ids=["cta_pair", "single_cta", "cta_pair_quad", "cta_pair_duo"])
 @pytest.mark.parametrize("case", TC_CASES, ids=[c[0] for c in TC_CASES])
 def test_conv3d_tcgen05(case, pair, monkeypatch):
     """The TMA/tcgen05 kernel against fp64 conv3d and against the generic tensor-core kernel (same numerics class).
@@ -454,7 +454,7 @@ def test_conv3d_tcgen05(case, pair, monkeypatch):
     cta_pair_quad: DPC_TC_QUAD=1, four output frames per tile with the temporal taps stacked into N = 64/128/192 MMAs."""
     _, B, Fr, H, W, C1, C2, Cout = case
     monkeypatch.setenv("DPC_TC_PAIR", "1" if pair else "0")
-    monkeypatch.setenv("DPC_TC_QUAD", "1" if pair == "quad" else "0")   # opt-in stacked-temporal-tap mode (Cout = 64 shapes)
+    monkeypatch.setenv("DPC_TC_QUAD", {"quad": "4", "duo": "2"}.get(pair, "0"))   # stacked-temporal-tap modes (Cout = 64 shapes)
     gen = g(21)
     x1 = torch.randn(B, Fr, H, W, C1, generator=gen)
     x2 = torch.randn(B, Fr, H, W, C2, generator=gen) if C2 else None
