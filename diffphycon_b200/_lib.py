@@ -32,6 +32,7 @@ class ConvParams(C.Structure):
         ("Hfull", C.c_int32), ("Wfull", C.c_int32), ("oh_mul", C.c_int32), ("oh_off", C.c_int32),
         ("ow_mul", C.c_int32), ("ow_off", C.c_int32),
         ("out_layout", C.c_int32), ("gn_groups", C.c_int32), ("precise", C.c_int32),
+        ("res_scale", c_fp), ("res_shift", c_fp),
     ]
 
 
@@ -68,6 +69,7 @@ _SIGNATURES = {
     "dpc_stem_conv_tcgen05": ([c_fp] * 4 + [C.c_int32] * 9 + [c_fp], C.c_int),
     "dpc_final_proj": ([c_fp] * 4 + [C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_spatial_attention_mma": ([c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
+    "dpc_gn_fold": ([c_fp] * 5 + [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_float, c_fp], C.c_int),
     "dpc_spatial_linear_attention": ([c_fp, c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_time_embed": ([c_fp] * 8 + [C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_time_proj": ([c_fp] * 4 + [C.c_int32] * 3 + [c_fp], C.c_int),
@@ -176,9 +178,10 @@ def _timed(label):
 
 
 @_timed("conv")
-def conv(params: ConvParams, tcgen05: bool = False) -> bool:
+def conv(params: ConvParams, tcgen05: bool = False, tc_only: bool = False) -> bool:
     """Launch a convolution.  With tcgen05=True tries the TMA/tcgen05 kernel first; returns True if it ran.
-    Falls back to the generic tensor-core implicit GEMM only on the documented 'shape not supported' code (-2)."""
+    Falls back to the generic tensor-core implicit GEMM only on the documented 'shape not supported' code (-2); with
+    tc_only=True nothing is launched in that case and False is returned."""
     L = lib()
     if tcgen05:
         rc = L.dpc_conv3d_tcgen05(C.byref(params), stream_ptr())
@@ -187,6 +190,8 @@ def conv(params: ConvParams, tcgen05: bool = False) -> bool:
             return True
         if rc != -2:
             check(rc, "dpc_conv3d_tcgen05")
+    if tc_only:
+        return False
     check(L.dpc_conv_igemm(C.byref(params), stream_ptr()), "dpc_conv_igemm")
     LaunchCounter.count += 1
     return False
@@ -198,6 +203,13 @@ def groupnorm_silu(y, stats, gamma, beta, scale_shift, ss_stride, ss_off, residu
     check(lib().dpc_groupnorm_silu(ptr(y), ptr(stats), ptr(gamma), ptr(beta), ptr(scale_shift), ss_stride, ss_off,
                                    ptr(residual), ptr(out), B, rows_per_sample, Cn, groups, eps, stream_ptr()),
           "dpc_groupnorm_silu")
+    LaunchCounter.count += 1
+
+
+@_timed("gn_fold")
+def gn_fold(stats, gamma, beta, scale, shift, B, rows_per_sample, Cn, groups, eps=1e-5):
+    check(lib().dpc_gn_fold(ptr(stats), ptr(gamma), ptr(beta), ptr(scale), ptr(shift), B, rows_per_sample, Cn, groups, eps,
+                            stream_ptr()), "dpc_gn_fold")
     LaunchCounter.count += 1
 
 

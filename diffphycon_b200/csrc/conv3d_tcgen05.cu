@@ -1,4 +1,6 @@
-// 3x3x3 / pad 1 Conv3d (Block.proj, conv3d.py:189-204) on the 5th-generation tensor cores of sm_100a.
+// 3x3x3 / pad 1 Conv3d (Block.proj, conv3d.py:189-204) on the 5th-generation tensor cores of sm_100a; the same kernel also
+// serves 1x1x1 convs / Linear layers ("gemm" mode), the 1x4x4 stride-2 down-conv and the ConvTranspose parity classes
+// (2x2-tap modes), cta_group::2 CTA pairs (PAIR) and the opt-in stacked-temporal-tap tiles (quad).
 //
 // Formulation: implicit GEMM, M = output voxels, N = Cout, K = 27 taps x Cin, TF32 operands, fp32 accumulate in TMEM.
 // The implicit-GEMM A operand re-reads every input voxel 27 times; fed tap-by-tap from L2 this kernel is bound by the
@@ -31,6 +33,8 @@ constexpr int APARTS = 3;           // the A box of a block is fetched as APARTS
 struct Params {
   const float* bias;
   const float* residual;      // optional, indexed like y
+  const float* res_scale;     // optional [B][ldy]: the residual enters as silu(residual * scale + shift) (folded GroupNorm + SiLU)
+  const float* res_shift;
   float* y;
   double* gn_stats;
   int B, F, H, W;
@@ -81,14 +85,6 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar_leader), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
 // Descriptors passed as (low word, high word): the per-MMA arithmetic only moves the 14-bit start-address field of the low
@@ -463,6 +459,17 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
             rnext[it] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (mu < p.H * p.W) rnext[it] = __ldcs(reinterpret_cast<const float4*>(p.residual + (frame_base + mu) * (size_t)p.ldy + ccol + cq));
           }
+          if (p.res_scale) {                               // GroupNorm-apply + SiLU of the residual branch, folded per (b, channel)
+            const float4 a4 = __ldg(reinterpret_cast<const float4*>(p.res_scale + (size_t)b * p.ldy + ccol + cq));
+            const float4 d4 = __ldg(reinterpret_cast<const float4*>(p.res_shift + (size_t)b * p.ldy + ccol + cq));
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              float t0 = fmaf(rnext[it].x, a4.x, d4.x), t1 = fmaf(rnext[it].y, a4.y, d4.y);
+              float t2 = fmaf(rnext[it].z, a4.z, d4.z), t3 = fmaf(rnext[it].w, a4.w, d4.w);
+              rnext[it] = make_float4(__fdividef(t0, 1.0f + __expf(-t0)), __fdividef(t1, 1.0f + __expf(-t1)),
+                                      __fdividef(t2, 1.0f + __expf(-t2)), __fdividef(t3, 1.0f + __expf(-t3)));
+            }
+          }
         };
         if (p.residual && eg < nitems) load_res(eg);
         for (int i = eg; i < nitems; i += 2) {
@@ -735,6 +742,7 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
                      c.Hfull == 2 * H && c.Wfull == 2 * W && (c.oh_off == 0 || c.oh_off == 1) && (c.ow_off == 0 || c.ow_off == 1) &&
                      c.ph == 1 - c.oh_off && c.pw == 1 - c.ow_off && W >= 4 && W + 1 <= 256;
   if (!conv_ok && !gemm_ok && !down_ok && !up_ok) return -2;
+  if ((c.res_scale || c.res_shift) && !(gemm_ok && !conv_ok && c.residual && c.res_scale && c.res_shift)) return -2;
   if (c.gn_stats && c.gn_groups != 8) return -2;   // the epilogue is specialised for GroupNorm(8), the reference default
   DPC_CHECK_ARG(c.x1 && c.w && c.y && (c.C2 == 0 || c.x2));
   const bool gemm = gemm_ok && !conv_ok;
@@ -744,7 +752,7 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   const bool pair = !gemm && mode == 0 && !(pair_env && atoi(pair_env) == 0) && ((int64_t)c.B * F) % 2 == 0;
   const int Ntile = gemm ? (c.Cout == 64 ? 64 : (c.Cout == 256 ? 256 : 128)) : c.Cout;
   Params p;
-  p.bias = c.bias; p.residual = c.residual; p.y = c.y; p.gn_stats = c.gn_stats; p.gn_groups = c.gn_groups;
+  p.bias = c.bias; p.residual = c.residual; p.res_scale = c.res_scale; p.res_shift = c.res_shift; p.y = c.y; p.gn_stats = c.gn_stats; p.gn_groups = c.gn_groups;
   p.B = c.B; p.F = F; p.H = mode == 1 ? c.Ho : H; p.W = mode == 1 ? c.Wo : W; p.C1 = c.C1; p.C2 = c.C2; p.Cout = c.Cout;
   p.mode = mode; p.cls_h = c.oh_off; p.cls_w = c.ow_off; p.Hout = c.Hfull; p.Wout = c.Wfull; p.o_mul = c.oh_mul;
   p.gemm = gemm ? 1 : 0;

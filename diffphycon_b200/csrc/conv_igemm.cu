@@ -345,6 +345,7 @@ extern "C" int dpc_conv_igemm(const dpc_conv_params* pp, void* stream) {
   DPC_CHECK_ARG(p.Npad % 64 == 0 && p.Kpad % BK == 0 && p.Cout <= p.Npad);
   DPC_CHECK_ARG(p.ntaps >= 1 && (int64_t)p.ntaps * (p.C1 + p.C2) <= p.Kpad);
   DPC_CHECK_ARG(p.out_layout == 0 || (p.residual == nullptr));
+  DPC_CHECK_ARG(p.res_scale == nullptr && p.res_shift == nullptr);   // the folded GroupNorm residual is a dpc_conv3d_tcgen05 feature
   DPC_CHECK_ARG(p.gn_stats == nullptr || (p.gn_groups > 0 && p.Cout % p.gn_groups == 0));
   const int64_t M64 = (int64_t)p.B * p.Fo * p.Ho * p.Wo;
   const int64_t Min = (int64_t)p.B * p.Fi * p.Hi * p.Wi;

@@ -254,6 +254,31 @@ extern "C" int dpc_groupnorm_silu(const float* y, const double* stats, const flo
   return 0;
 }
 
+__global__ void __launch_bounds__(256)
+gn_fold_kernel(const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+               float* __restrict__ scale, float* __restrict__ shift, int B, int64_t rows_per_sample, int C, int groups, float eps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C, cpg = C / groups, g = c / cpg;
+  const double inv_n = 1.0 / ((double)rows_per_sample * (double)cpg);
+  const double mean = stats[((size_t)b * groups + g) * 2] * inv_n;
+  double var = stats[((size_t)b * groups + g) * 2 + 1] * inv_n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float a = (float)(1.0 / sqrt(var + (double)eps)) * gamma[c];
+  scale[i] = a;
+  shift[i] = fmaf(-(float)mean, a, beta[c]);
+}
+
+extern "C" int dpc_gn_fold(const double* stats, const float* gamma, const float* beta, float* scale, float* shift, int32_t B,
+                           int64_t rows_per_sample, int32_t C, int32_t groups, float eps, void* stream) {
+  using namespace dpc;
+  DPC_CHECK_ARG(stats && gamma && beta && scale && shift && B > 0 && rows_per_sample > 0 && C > 0 && groups > 0 && C % groups == 0);
+  gn_fold_kernel<<<(unsigned)((B * C + 255) / 256), 256, 0, (cudaStream_t)stream>>>(stats, gamma, beta, scale, shift, B,
+                                                                                     rows_per_sample, C, groups, eps);
+  DPC_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int dpc_layernorm_channels(const float* x, const float* gamma, const float* residual, float* out, int64_t rows,
                                       int32_t C, float eps, int32_t use_rsqrt, void* stream) {
   using namespace dpc;

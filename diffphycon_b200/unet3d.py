@@ -465,13 +465,14 @@ class Unet3D_with_Conv3D(nn.Module):
             return s
 
         def conv(xa, ca, w, bias, y, cout, lvl_in, kind, xb=None, cb=0, residual=None, gn=None, out_layout=0,
-                 transposed_cls=None, tc=False):
+                 transposed_cls=None, tc=False, res_affine=None, tc_only=False):
             hi, wi = G[f"hw.{lvl_in}"]
             p = _lib.ConvParams()
             p.x1, p.x2 = xa.data_ptr(), (xb.data_ptr() if xb is not None else None)
             p.C1, p.C2 = ca, cb
             p.w, p.bias = w.data_ptr(), (bias.data_ptr() if bias is not None else None)
             p.residual = residual.data_ptr() if residual is not None else None
+            p.res_scale, p.res_shift = (res_affine[0].data_ptr(), res_affine[1].data_ptr()) if res_affine is not None else (None, None)
             p.y = y.data_ptr()
             p.gn_stats = gn.data_ptr() if gn is not None else None
             p.gn_groups = groups if gn is not None else 0
@@ -507,7 +508,7 @@ class Unet3D_with_Conv3D(nn.Module):
             p.Cout, p.Npad, p.Kpad = cout, w.shape[0], w.shape[1]
             p.out_layout = out_layout
             p.precise = 1 if precise else 0
-            _lib.conv(p, tcgen05=tc and not precise)
+            return _lib.conv(p, tcgen05=tc and not precise, tc_only=tc_only)
 
         ss = None  # [B, total] time scale/shift for every ResnetBlock
 
@@ -526,6 +527,20 @@ class Unet3D_with_Conv3D(nn.Module):
             conv(y1, cout, P[f"{name}.block2.w"], P[f"{name}.block2.b"], y2, cout, lvl, "333", gn=s2,
                  tc=self.use_tcgen05)
             pool.put(y1)
+            if f"{name}.res.w" in P and self.use_tcgen05 and not precise:
+                # block2's GroupNorm-apply + SiLU folded into the residual operand of the res_conv GEMM (one pass instead of
+                # res_conv -> res, then norm(y2) + res): out = silu(GN(y2)) + res_conv(x)
+                ga, gd = pool.get(B * cout), pool.get(B * cout)
+                _lib.gn_fold(s2, P[f"{name}.block2.gamma"], P[f"{name}.block2.beta"], ga, gd, B, rps, cout, groups)
+                outb = pool.get(m * cout)
+                ok = conv(xa, ca, P[f"{name}.res.w"], P[f"{name}.res.b"], outb, cout, lvl, "111", xb=xb, cb=cb, residual=y2,
+                          res_affine=(ga, gd), tc=True, tc_only=True)
+                pool.put(ga)
+                pool.put(gd)
+                if ok:
+                    pool.put(y2)
+                    return outb
+                pool.put(outb)
             if f"{name}.res.w" in P:
                 res = pool.get(m * cout)
                 conv(xa, ca, P[f"{name}.res.w"], P[f"{name}.res.b"], res, cout, lvl, "111", xb=xb, cb=cb, tc=self.use_tcgen05)

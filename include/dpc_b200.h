@@ -67,6 +67,10 @@ typedef struct dpc_conv_params {
   int32_t out_layout;
   int32_t gn_groups;
   int32_t precise;   /* 1 = 3xTF32 error-compensated product (near-fp32), 0 = plain TF32 */
+  /* optional (dpc_conv3d_tcgen05, 1x1x1 only): the residual enters as silu(residual * res_scale[b][c] + res_shift[b][c]), i.e. a
+   * GroupNorm-apply + SiLU folded into per-(sample, channel) coefficients by dpc_gn_fold: ResnetBlock's
+   * block2-norm-act + res_conv(x) (conv3d.py:197-204, :229-230) in one pass.  [B][Cout] each; NULL = plain residual. */
+  const float* res_scale; const float* res_shift;
 } dpc_conv_params;
 
 int dpc_conv_igemm(const dpc_conv_params* p, void* stream);
@@ -103,6 +107,10 @@ int dpc_groupnorm_silu(const float* y, const double* stats, const float* gamma, 
 /* Channel LayerNorm, gain only, over C for every row (+ optional residual added after the gain):
  * use_rsqrt 0: (x-mean)/sqrt(var+eps)*gamma  — conv3d.py:165-174;
  * use_rsqrt 1: (x-mean)*rsqrt(var+eps)*gamma — the 2-D variants, model/burgers_1d/unet.py:60-70. */
+/* Folds GroupNorm statistics into per-(sample, channel) affine coefficients: scale = rstd*gamma, shift = beta - mean*rstd*gamma
+ * (stats as produced by the conv epilogues: [B][groups][2] doubles = sum, sum of squares over rows_per_sample*C/groups values). */
+int dpc_gn_fold(const double* stats, const float* gamma, const float* beta, float* scale, float* shift, int32_t B,
+                int64_t rows_per_sample, int32_t C, int32_t groups, float eps, void* stream);
 int dpc_layernorm_channels(const float* x, const float* gamma, const float* residual, float* out, int64_t rows,
                            int32_t C, float eps, int32_t use_rsqrt, void* stream);
 

@@ -25,7 +25,7 @@ def _view(ptr, numel, dtype=np.float32):
     return torch.from_numpy(arr)
 
 
-def conv(p, tcgen05=False):
+def conv(p, tcgen05=False, tc_only=False):
     B, Fi, Hi, Wi, C1, C2 = p.B, p.Fi, p.Hi, p.Wi, p.C1, p.C2
     Fo, Ho, Wo = p.Fo, p.Ho, p.Wo
     cin = C1 + C2
@@ -59,8 +59,12 @@ def conv(p, tcgen05=False):
     if p.out_layout == 0:
         y = _view(p.y, B * Fo * Hf * Wf * p.Cout).reshape(B, Fo, Hf, Wf, p.Cout)
         if p.residual:
-            r = _view(p.residual, B * Fo * Hf * Wf * p.Cout).reshape(B, Fo, Hf, Wf, p.Cout)
-            acc += r[:, :, hs, ws].double()
+            r = _view(p.residual, B * Fo * Hf * Wf * p.Cout).reshape(B, Fo, Hf, Wf, p.Cout)[:, :, hs, ws].double()
+            if p.res_scale:                                   # folded GroupNorm-apply + SiLU of the residual branch
+                a = _view(p.res_scale, B * p.Cout).reshape(B, 1, 1, 1, p.Cout).double()
+                d = _view(p.res_shift, B * p.Cout).reshape(B, 1, 1, 1, p.Cout).double()
+                r = torch.nn.functional.silu(r * a + d)
+            acc += r
         y[:, :, hs, ws] = acc.float()
     else:
         y = _view(p.y, B * Fo * Hf * Wf * p.Cout).reshape(B, Fo, p.Cout, Hf, Wf)
@@ -90,6 +94,18 @@ def groupnorm_silu(y, stats, gamma, beta, scale_shift, ss_stride, ss_off, residu
     if residual is not None:
         t = t + residual[: B * rps * Cn].reshape(B, rps, Cn)
     out[: B * rps * Cn] = t.reshape(-1)
+
+
+def gn_fold(stats, gamma, beta, scale, shift, B, rps, Cn, groups, eps=1e-5):
+    st = stats[: B * groups * 2].reshape(B, groups, 2).double()
+    n = rps * (Cn // groups)
+    mean = st[:, :, 0] / n
+    var = (st[:, :, 1] / n - mean * mean).clamp(min=0)
+    rstd = (1.0 / (var + eps).sqrt()).repeat_interleave(Cn // groups, dim=1)
+    mean = mean.repeat_interleave(Cn // groups, dim=1)
+    a = rstd * gamma.double()[None, :]
+    scale[: B * Cn] = a.float().reshape(-1)
+    shift[: B * Cn] = (beta.double()[None, :] - mean * a).float().reshape(-1)
 
 
 def layernorm_channels(x, gamma, out, rows, Cn, eps=1e-5, residual=None, use_rsqrt=False):
@@ -344,7 +360,7 @@ def jelly_write_bd(pred_bd, bd_0, x_next, x_w, cond_steps):
     x_w[:, :, 3:6] = bd
 
 
-EMULATED = ("temporal_block_fused", "final_proj", "spatial_linear_block_fused", "stem_conv", "jelly_x_start", "jelly_step", "jelly_write_bd", "burgers_model_output", "ddpm_posterior_step", "conv", "groupnorm_silu", "layernorm_channels", "pack_input", "temporal_attention", "spatial_attention",
+EMULATED = ("temporal_block_fused", "gn_fold", "final_proj", "spatial_linear_block_fused", "stem_conv", "jelly_x_start", "jelly_step", "jelly_write_bd", "burgers_model_output", "ddpm_posterior_step", "conv", "groupnorm_silu", "layernorm_channels", "pack_input", "temporal_attention", "spatial_attention",
             "spatial_linear_attention", "time_embed", "time_proj", "predict_x_start", "guided_step", "upsample_nearest2x")
 
 

@@ -45,7 +45,7 @@ def test_struct_layouts_match_header():
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     names = re.findall(r"[\s\*,]([A-Za-z_][A-Za-z0-9_]*)\s*(?=[;,])", body)
     assert names == [f[0] for f in _lib.ConvParams._fields_]
-    assert ctypes.sizeof(_lib.ConvParams) == 8 * 8 + 4 * 28
+    assert ctypes.sizeof(_lib.ConvParams) == 8 * 8 + 4 * 28 + 2 * 8
     assert ctypes.sizeof(_lib.StepCoefs) == 4 * 19
 
 

@@ -510,6 +510,42 @@ def test_linear_tcgen05(case):
     assert rel_err(y, ref) <= TOL_TF32
 
 
+@pytest.mark.parametrize("B,Fr,S,C1,C2,Cout", [(2, 4, 16, 128, 0, 64), (3, 2, 32, 64, 64, 64), (1, 4, 16, 256, 256, 128), (2, 3, 8, 64, 0, 128)])
+def test_linear_tcgen05_folded_groupnorm_residual(B, Fr, S, C1, C2, Cout):
+    """ResnetBlock tail in one pass (conv3d.py:229-230): out = silu(GroupNorm(y2)) + res_conv(x).  dpc_gn_fold turns the conv
+    epilogue's statistics into per-(sample, channel) coefficients; the 1x1x1 GEMM applies them to its residual operand."""
+    gen = g(61)
+    x1 = torch.randn(B, Fr, S, S, C1, generator=gen)
+    x2 = torch.randn(B, Fr, S, S, C2, generator=gen) if C2 else None
+    y2 = torch.randn(B, Fr, S, S, Cout, generator=gen) * 1.7 + 0.4
+    w = torch.randn(Cout, C1 + C2, generator=gen) / (C1 + C2) ** 0.5
+    bias, gamma, beta = (torch.randn(Cout, generator=gen) for _ in range(3))
+    xin = torch.cat([x1, x2], -1) if C2 else x1
+    gn = F.group_norm(y2.reshape(B, -1, Cout).permute(0, 2, 1).double(), 8, gamma.double(), beta.double(), eps=1e-5)
+    ref = F.silu(gn).permute(0, 2, 1).reshape(B, Fr, S, S, Cout) + xin.double() @ w.double().t() + bias.double()
+    v = y2.double().reshape(B, -1, 8, Cout // 8)
+    stats = torch.stack([v.sum(dim=(1, 3)), (v * v).sum(dim=(1, 3))], dim=-1).contiguous().to(DEV)
+    a, d = torch.empty(B, Cout, device=DEV), torch.empty(B, Cout, device=DEV)
+    _lib.gn_fold(stats, gamma.to(DEV), beta.to(DEV), a, d, B, Fr * S * S, Cout, 8)
+    p = _lib.ConvParams()
+    x1d, y2d, wp, bd = x1.to(DEV), y2.to(DEV), packing.pack_linear(w.to(DEV)), bias.to(DEV)
+    x2d = x2.to(DEV) if C2 else None
+    taps = packing.tap_table(1, 1, 1, S, S, DEV)
+    out = torch.full((B, Fr, S, S, Cout), float("nan"), device=DEV)
+    p.x1, p.C1, p.x2, p.C2 = x1d.data_ptr(), C1, (x2d.data_ptr() if C2 else None), C2
+    p.w, p.bias, p.residual, p.y = wp.data_ptr(), bd.data_ptr(), y2d.data_ptr(), out.data_ptr()
+    p.res_scale, p.res_shift = a.data_ptr(), d.data_ptr()
+    p.taps, p.ntaps = taps.data_ptr(), 1
+    p.B, p.Fi, p.Hi, p.Wi, p.Fo, p.Ho, p.Wo = B, Fr, S, S, Fr, S, S
+    p.st = p.sh = p.sw = 1
+    p.oh_mul = p.ow_mul = 1
+    p.Hfull, p.Wfull = S, S
+    p.Cout, p.Npad, p.Kpad = Cout, wp.shape[0], wp.shape[1]
+    assert _lib.conv(p, tcgen05=True, tc_only=True)
+    torch.cuda.synchronize()
+    assert rel_err(out, ref) <= TOL_TF32
+
+
 @pytest.mark.parametrize("ddim", [False, True])
 @pytest.mark.parametrize("guided", [False, True])
 def test_jellyfish_step_kernels_match_torch_restatement(ddim, guided):
