@@ -69,6 +69,7 @@ _SIGNATURES = {
     "dpc_stem_conv_tcgen05": ([c_fp] * 4 + [C.c_int32] * 9 + [c_fp], C.c_int),
     "dpc_final_proj": ([c_fp] * 4 + [C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_spatial_attention_mma": ([c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
+    "dpc_smoke_eval_sums": ([c_fp] * 5 + [C.c_int32] * 6 + [c_fp], C.c_int),
     "dpc_gn_fold": ([c_fp] * 5 + [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_float, c_fp], C.c_int),
     "dpc_spatial_linear_attention": ([c_fp, c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_time_embed": ([c_fp] * 8 + [C.c_int32, C.c_int32, c_fp], C.c_int),
@@ -340,6 +341,12 @@ def smoke_rollout(fluid_mask, velocity_mask, init_velocity, init_density, c1, c2
                                   ptr(vel_ws), ptr(x_ws), ptr(dens_ws), ptr(densitys), ptr(zero_densitys), ptr(velocitys),
                                   ptr(smoke_out), ptr(iterations), B, nt, nx, T, float(dt), float(accuracy),
                                   int(max_iterations), stream_ptr()), "dpc_smoke_rollout")
+    LaunchCounter.count += 1
+
+
+def smoke_eval_sums(pred, densitys, velocitys, smoke_out, sums, B, F, S, T, mask_lo, mask_hi):
+    check(lib().dpc_smoke_eval_sums(ptr(pred), ptr(densitys), ptr(velocitys), ptr(smoke_out), ptr(sums), B, F, S, T, mask_lo,
+                                    mask_hi, stream_ptr()), "dpc_smoke_eval_sums")
     LaunchCounter.count += 1
 
 

@@ -243,6 +243,13 @@ int dpc_smoke_rollout(const int8_t* fluid_mask, const float* velocity_mask, cons
                       int32_t* iterations, int32_t B, int32_t nt, int32_t nx, int32_t T, double dt, double accuracy,
                       int32_t max_iterations, void* stream);
 
+/* Evaluation-stage sums of InferencePipeline.multi_evaluate (inference/inference_2d_smoke.py:384-416) taken from the rollout
+ * outputs: pred [B][F][6][S][S] against data_current = (density, velocity x/y, masked sampled controls, smoke portion) at frames
+ * t = f*T/F and pixels (y*128/S, x*128/S), frame 0 excluded.  The sampled controls count as zero inside [mask_lo, mask_hi)^2
+ * (:322).  sums [B][12] doubles: 0..5 sum (pred_c - data_c)^2; 6..10 sum data_c^2 (c = 0..4); 11 sum of pred[:, F-1, 5]. */
+int dpc_smoke_eval_sums(const float* pred, const float* densitys, const double* velocitys, const double* smoke_out,
+                        double* sums, int32_t B, int32_t F, int32_t S, int32_t T, int32_t mask_lo, int32_t mask_hi, void* stream);
+
 /* Burgers sampler, elementwise parts of diffusion/diffusion_1d_burgers.py:396-470 on [B,C,H,W] tensors (n elements,
  * `plane` = H*W): dpc_burgers_model_output combines the joint and prior network outputs (mode 0: eps1 - coef*eps2',
  * mode 1: (eps1 - coef*eps2')/beta, mode 2: (beta*eps1)'; ' zeroes channel 0, :403, :414) and predicts x_start (:425);
