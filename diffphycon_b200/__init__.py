@@ -11,6 +11,7 @@ Sub-modules mirror the other reference modules of the path:
     smoke_rollout.{init_sim_128, init_velocity_, solver}   dataset/apps/evaluate_solver.py
     burgers.burgers_numeric_solve_free          dataset/apps/generate_burgers.py:207
     data_smoke.Smoke                            dataset/data_2d.py:139
+    burgers_metric.burgers_metric               utils.py:1203
     evaluate.multi_evaluate                     inference/inference_2d_smoke.py:317-427 (InferencePipeline.multi_evaluate)
     checkpoint.{load_trainer_checkpoint, load_ddpm_model}   Trainer.load (diffusion_2d_smoke.py:958-985), inference_2d_smoke.py:46-127
 The arithmetic lives in libdpc_b200.so (include/dpc_b200.h); there is no CPU or PyTorch fallback.
