@@ -113,3 +113,54 @@ def test_ddim_loop_matches_reference(golden_dir):
                             design_guidance="standard", standard_fixed_ratio=1e5, coeff_ratio=0.0, w_prob_exp=0.97)
     ref = torch.from_numpy(z["y"])
     assert (x - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+
+
+# ---- the benchmarked shape (smoke 64x64, 32 frames, dim 64 (1,2,4)): tests/golden/make_golden_metric_shape.py ----------
+METRIC_SEEDS = {"joint": (6, 31), "prior": (2, 33)}
+
+
+def metric_input(channels, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(1, 32, channels, 64, 64, generator=g)
+
+
+@pytest.mark.parametrize("tag", ["joint", "prior"])
+def test_unet_oracle_matches_reference_at_metric_shape(tag, golden_dir):
+    """The oracle against strided subsamples of the UNMODIFIED reference's output and stage activations at
+    [1,32,C,64,64] — the shape bench.py measures."""
+    z = np.load(os.path.join(golden_dir, "metric_shape.npz"))
+    ch, seed = METRIC_SEEDS[tag]
+    cfg = uo.UnetCfg(dim=64, dim_mults=(1, 2, 4), channels=ch)
+    taps = {}
+    y = uo.forward(uo.make_params(cfg, seed), cfg, metric_input(ch, seed + 1), torch.tensor([int(z[f"{tag}/t"])]), taps=taps)
+    ref = torch.from_numpy(z[f"{tag}/y"])
+    assert (y[:, ::8, :, ::8, ::8] - ref).abs().max().item() <= TOL * max(1.0, float(z[f"{tag}/y_absmax"]))
+    for k in z.files:
+        if k.startswith(f"{tag}/act/") and k.split("/", 2)[2] in taps:
+            nm = k.split("/", 2)[2]
+            a = torch.from_numpy(z[k])
+            err = (taps[nm][:, :, ::8, ::8, ::8] - a).abs().max().item()
+            assert err <= TOL * max(1.0, float(z[f"{tag}/absmax/{nm}"])), (nm, err)
+
+
+def test_p_sample_oracle_matches_reference_at_metric_shape(golden_dir):
+    z = np.load(os.path.join(golden_dir, "metric_shape.npz"))
+    t = int(z["p_sample/t"])
+    cj = uo.UnetCfg(dim=64, dim_mults=(1, 2, 4), channels=6)
+    cw = uo.UnetCfg(dim=64, dim_mults=(1, 2, 4), channels=2)
+    init = torch.from_numpy(z["p_sample/init"])
+    x = metric_input(6, 78)
+    x[:, 0, 0] = init
+    tt = torch.tensor([t])
+    ej = uo.forward(uo.make_params(cj, 31), cj, x, tt)
+    ew = uo.forward(uo.make_params(cw, 33), cw, x[:, :, 3:5], tt)
+    torch.manual_seed(1234 + t)
+    noise = torch.randn(1, 32, 6, 64, 64)
+    R = torch.tensor(so.SMOKE_RESCALER).reshape(1, 1, 6, 1, 1)
+    sched = so.make_schedule(1000, "sigmoid")
+    pred, x_start = so.p_sample_step(sched, x, t, ej, ew, noise, init, _design(R, 0.0), design_guidance="standard",
+                                     standard_fixed_ratio=1e5, coeff_ratio=0.0, w_prob_exp=0.97)
+    # an eps difference d moves x_start by sqrt(1/abar_t - 1) * d (smoke.py:576-580); 2e-5 oracle-vs-reference noise on eps
+    amp = float(sched["sqrt_recipm1_alphas_cumprod"][t])
+    assert (x_start[:, ::8, :, ::8, ::8] - torch.from_numpy(z["p_sample/x_start"])).abs().max().item() <= TOL * amp + 1e-6
+    assert (pred[:, ::8, :, ::8, ::8] - torch.from_numpy(z["p_sample/pred"])).abs().max().item() <= TOL * amp + 1e-6

@@ -1,6 +1,7 @@
 """GPU parity of the whole U-Net forward (through the C-ABI kernels) against the golden vectors produced by the
 unmodified reference, in both numerics modes, plus size-independent properties at the metric configuration's shape.
-  tf32   : contraction-class tolerance 1e-2 of the output scale (54 chained TF32 convs, 10-bit mantissa operands)
+  tf32   : contraction-class tolerance 3e-3 of the output scale (54 chained TF32 convs, 10-bit mantissa operands; measured
+           1.1e-3 - 1.3e-3 on these cases)
   3xtf32 : fp32-class tolerance 2e-4"""
 import os
 
@@ -19,7 +20,7 @@ CASES = {
     "unet_smoke_arch": dict(dim=64, dim_mults=(1, 2, 4), channels=6),
     "unet_jelly_arch": dict(dim=32, dim_mults=(1, 2), channels=7, out_dim=4),
 }
-TOL = {"tf32": 1e-2, "3xtf32": 2e-4}
+TOL = {"tf32": 3e-3, "3xtf32": 2e-4}
 
 
 def build(name, seed, precision, tcgen05=True):
@@ -111,10 +112,10 @@ def test_metric_shape_forward_properties():
     assert (y - y_generic).abs().max().item() <= 2e-3 * max(1.0, scale)
 
 
-@pytest.mark.parametrize("frames,size,channels,out_dim", [(64, 128, 6, None), (20, 128, 7, 4), (5, 64, 6, None), (32, 32, 2, None)])
+@pytest.mark.parametrize("frames,size,channels,out_dim", [(5, 64, 6, None), (32, 32, 2, None)])
 def test_other_config_shapes_forward_properties(frames, size, channels, out_dim):
-    """The other BASELINE.json configurations' shapes at batch 1 (128x128 with 64 frames = config 5, the jellyfish 20-frame
-    128x128 network = config 3) plus an odd frame count (no CTA pairs) and a small frame: finite, deterministic, and the tcgen05
+    """An odd frame count (no CTA pairs) and a small frame (the BASELINE.json shapes of configs 3 and 5 are compared with the
+    oracle in tests/test_metric_shape_gpu.py): finite, deterministic, and the tcgen05
     path (pairs, fused blocks where their shape gates admit them, stem / down / transposed kernels) equals the generic
     tensor-core path within TF32 accumulation-order noise."""
     kw = dict(dim=64, dim_mults=(1, 2, 4), channels=channels)
