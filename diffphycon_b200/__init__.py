@@ -4,6 +4,8 @@ Public surface (mirrors the reference modules named in SURVEY.md section 8(b)):
     Unet3D_with_Conv3D          model/video_diffusion_pytorch/video_diffusion_pytorch_conv3d.py:356
     GaussianDiffusion           diffusion/diffusion_2d_smoke.py:451
     StockSmokeGuidance          inference/inference_2d_smoke.py:30-44 (closed-form, fused into the step kernel)
+    Unet, ForceUnet, JellyfishGuidance   diffusion/diffusion_2d_jellyfish.py:276-481 (boundary updater, force surrogate) and
+                                inference/inference_2d_jellyfish.py:85-114, :276-279 (force_fn / design_fn): forward AND backward
 Sub-modules mirror the other reference modules of the path:
     diffusion_2d_jellyfish.GaussianDiffusion    diffusion/diffusion_2d_jellyfish.py:529
     diffusion_1d_burgers.GaussianDiffusion, get_nablaJ, cosine_beta_J_schedule, ...   diffusion/diffusion_1d_burgers.py
@@ -17,6 +19,8 @@ Sub-modules mirror the other reference modules of the path:
 The arithmetic lives in libdpc_b200.so (include/dpc_b200.h); there is no CPU or PyTorch fallback.
 """
 from .diffusion_2d_smoke import SMOKE_RESCALER, GaussianDiffusion, StockSmokeGuidance  # noqa: F401
+from .jellyfish_nets import ForceUnet, JellyfishGuidance, Unet  # noqa: F401
 from .unet3d import Unet3D_with_Conv3D  # noqa: F401
 
-__all__ = ["Unet3D_with_Conv3D", "GaussianDiffusion", "StockSmokeGuidance", "SMOKE_RESCALER"]
+__all__ = ["Unet3D_with_Conv3D", "GaussianDiffusion", "StockSmokeGuidance", "SMOKE_RESCALER", "Unet", "ForceUnet",
+           "JellyfishGuidance"]

@@ -5,7 +5,9 @@ used only for device memory and streams; every function here takes torch CUDA te
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
+import functools
 import os
 
 import torch
@@ -85,6 +87,18 @@ _SIGNATURES = {
     "dpc_jelly_step": ([c_fp] * 12 + [C.c_float] * 5 + [C.c_int32] * 4 + [C.c_int64, c_fp], C.c_int),
     "dpc_jelly_write_bd": ([c_fp] * 4 + [C.c_int32] * 3 + [C.c_int64, c_fp], C.c_int),
     "dpc_burgers_rollout": ([c_fp] * 3 + [C.c_int32] * 4 + [C.c_float] * 6 + [c_fp], C.c_int),
+    "dpc_spatial_linear_attention_ex": ([c_fp] * 4 + [C.c_int32] * 3 + [C.c_float, c_fp], C.c_int),
+    "dpc_linattn2d_bwd": ([c_fp] * 6 + [C.c_int32] * 3 + [C.c_float, C.c_float, c_fp], C.c_int),
+    "dpc_attention2d_bwd": ([c_fp] * 4 + [C.c_int32] * 3 + [C.c_float, c_fp], C.c_int),
+    "dpc_gn_silu_bwd": ([c_fp] * 5 + [C.c_int64, C.c_int64] + [c_fp] * 4 + [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_float,
+                                                                         c_fp], C.c_int),
+    "dpc_layernorm_channels_bwd": ([c_fp] * 5 + [C.c_int64, C.c_int32, C.c_float, C.c_int32, c_fp], C.c_int),
+    "dpc_add": ([c_fp] * 3 + [C.c_int64, c_fp], C.c_int),
+    "dpc_sumpool2x2": ([c_fp, c_fp, C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
+    "dpc_mean_head": ([c_fp] * 4 + [C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
+    "dpc_mean_head_bwd": ([c_fp] * 3 + [C.c_int64, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
+    "dpc_time_embed_f32": ([c_fp] * 8 + [C.c_int32, C.c_int32, c_fp], C.c_int),
+    "dpc_time_mlp_bwd": ([c_fp] * 9 + [C.c_int32] * 3 + [c_fp], C.c_int),
     "dpc_smoke_rollout": ([c_fp] * 14 + [C.c_int32] * 4 + [C.c_double, C.c_double, C.c_int32, c_fp], C.c_int),
 }
 
@@ -119,14 +133,43 @@ def check(rc: int, what: str):
 
 
 def ptr(t):
+    """Raw device pointer of a contiguous CUDA tensor that lives on the CURRENT device (kernels are launched on the current
+    device's current stream: a tensor of another device would be dereferenced on the wrong GPU)."""
     if t is None:
         return None
     assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    if t.device.index != torch.cuda.current_device():
+        raise RuntimeError(f"tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                           "call through the module API (it makes the tensors' device current) or use torch.cuda.device(...)")
     return t.data_ptr()
 
 
 def stream_ptr():
+    """The current stream of the current device; the module entry points run under `on_device(tensor)`."""
     return torch.cuda.current_stream().cuda_stream
+
+
+def on_device(t):
+    """Context manager that makes the device of `t` (a tensor or a torch.device) current for the launches inside."""
+    dev = t.device if isinstance(t, torch.Tensor) else torch.device(t)
+    return torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()
+
+
+def device_guarded(fn):
+    """Decorator for the public entry points: the device of the first CUDA tensor argument is made current for the call,
+    so that `stream_ptr()` / the per-device launch state on the C side belong to the device the data lives on."""
+    @functools.wraps(fn)
+    def wrapper(*a, **k):
+        for v in a:
+            if isinstance(v, torch.Tensor) and v.is_cuda:
+                with torch.cuda.device(v.device):
+                    return fn(*a, **k)
+        for v in k.values():
+            if isinstance(v, torch.Tensor) and v.is_cuda:
+                with torch.cuda.device(v.device):
+                    return fn(*a, **k)
+        return fn(*a, **k)
+    return wrapper
 
 
 class LaunchCounter:
@@ -396,4 +439,82 @@ def jelly_write_bd(pred_bd, bd_0, x_next, x_w, cond_steps):
     B, F, _, H, W = x_next.shape
     check(lib().dpc_jelly_write_bd(ptr(pred_bd), ptr(bd_0), ptr(x_next), ptr(x_w), B, F, cond_steps, H * W, stream_ptr()),
           "dpc_jelly_write_bd")
+    LaunchCounter.count += 1
+
+
+# ---- jellyfish surrogate networks (include/dpc_b200.h, "Jellyfish surrogate networks") -------------------------------------
+ATT_SCALE = 32 ** -0.5
+
+
+@_timed("spatial_linear_attention")
+def spatial_linear_attention_ex(qkv, ctx_ws, kstat, out, BF, HW, heads, v_scale):
+    check(lib().dpc_spatial_linear_attention_ex(ptr(qkv), ptr(ctx_ws), ptr(kstat), ptr(out), BF, HW, heads, v_scale, stream_ptr()),
+          "dpc_spatial_linear_attention_ex")
+    LaunchCounter.count += 2
+
+
+@_timed("linattn2d_bwd")
+def linattn2d_bwd(qkv, ctx, kstat, dout, dctx_ws, dqkv, BF, HW, heads, v_scale):
+    check(lib().dpc_linattn2d_bwd(ptr(qkv), ptr(ctx), ptr(kstat), ptr(dout), ptr(dctx_ws), ptr(dqkv), BF, HW, heads, ATT_SCALE,
+                                  v_scale, stream_ptr()), "dpc_linattn2d_bwd")
+    LaunchCounter.count += 2
+
+
+@_timed("attention2d_bwd")
+def attention2d_bwd(qkv, out, dout, dqkv, BF, HW, heads):
+    check(lib().dpc_attention2d_bwd(ptr(qkv), ptr(out), ptr(dout), ptr(dqkv), BF, HW, heads, ATT_SCALE, stream_ptr()),
+          "dpc_attention2d_bwd")
+    LaunchCounter.count += 1
+
+
+@_timed("gn_silu_bwd")
+def gn_silu_bwd(y, stats, gamma, beta, scale_shift, ss_stride, ss_off, dout, dy, sums_ws, dss, B, rows_per_sample, Cn, groups,
+                eps=1e-5):
+    check(lib().dpc_gn_silu_bwd(ptr(y), ptr(stats), ptr(gamma), ptr(beta), ptr(scale_shift), ss_stride, ss_off, ptr(dout), ptr(dy),
+                                ptr(sums_ws), ptr(dss), B, rows_per_sample, Cn, groups, eps, stream_ptr()), "dpc_gn_silu_bwd")
+    LaunchCounter.count += 2
+
+
+@_timed("layernorm_channels_bwd")
+def layernorm_channels_bwd(x, gamma, dy, add, dx, rows, Cn, eps=1e-5, use_rsqrt=True):
+    check(lib().dpc_layernorm_channels_bwd(ptr(x), ptr(gamma), ptr(dy), ptr(add), ptr(dx), rows, Cn, eps, 1 if use_rsqrt else 0,
+                                           stream_ptr()), "dpc_layernorm_channels_bwd")
+    LaunchCounter.count += 1
+
+
+@_timed("add")
+def add(a, b, out, n):
+    check(lib().dpc_add(ptr(a), ptr(b), ptr(out), n, stream_ptr()), "dpc_add")
+    LaunchCounter.count += 1
+
+
+@_timed("sumpool2x2")
+def sumpool2x2(dy, dx, N, H, W, Cn):
+    check(lib().dpc_sumpool2x2(ptr(dy), ptr(dx), N, H, W, Cn, stream_ptr()), "dpc_sumpool2x2")
+    LaunchCounter.count += 1
+
+
+@_timed("mean_head")
+def mean_head(x, W, bias, out, N, HW, Cn, O):
+    check(lib().dpc_mean_head(ptr(x), ptr(W), ptr(bias), ptr(out), N, HW, Cn, O, stream_ptr()), "dpc_mean_head")
+    LaunchCounter.count += 1
+
+
+@_timed("mean_head_bwd")
+def mean_head_bwd(dout, W, dx, N, HW, Cn, O):
+    check(lib().dpc_mean_head_bwd(ptr(dout), ptr(W), ptr(dx), N, HW, Cn, O, stream_ptr()), "dpc_mean_head_bwd")
+    LaunchCounter.count += 1
+
+
+@_timed("time_embed")
+def time_embed_f32(t, freqs, w1, b1, w2, b2, hidden_ws, t_emb, B, dim):
+    check(lib().dpc_time_embed_f32(ptr(t), ptr(freqs), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(hidden_ws), ptr(t_emb), B, dim,
+                                   stream_ptr()), "dpc_time_embed_f32")
+    LaunchCounter.count += 2
+
+
+@_timed("time_mlp_bwd")
+def time_mlp_bwd(t, freqs, w1, b1, w2, w_proj, t_emb, dss, dt, B, dim, total):
+    check(lib().dpc_time_mlp_bwd(ptr(t), ptr(freqs), ptr(w1), ptr(b1), ptr(w2), ptr(w_proj), ptr(t_emb), ptr(dss), ptr(dt), B, dim,
+                                 total, stream_ptr()), "dpc_time_mlp_bwd")
     LaunchCounter.count += 1

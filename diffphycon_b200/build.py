@@ -11,7 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libdpc_b200.so")
 STAMP = os.path.join(HERE, ".build_stamp")
 SOURCES = ["lib.cu", "smoke_rollout.cu", "burgers_rollout.cu", "conv_igemm.cu", "conv3d_tcgen05.cu", "norm_act.cu", "attention.cu", "time_embed.cu",
-           "sampler_step.cu", "jellyfish_step.cu", "temporal_block_tcgen05.cu", "spatial_linear_block_tcgen05.cu", "stem_conv_tcgen05.cu", "smoke_eval.cu"]
+           "sampler_step.cu", "jellyfish_step.cu", "temporal_block_tcgen05.cu", "spatial_linear_block_tcgen05.cu", "stem_conv_tcgen05.cu", "smoke_eval.cu", "nets2d.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
               "-Xcompiler", "-fPIC"]
 

@@ -12,6 +12,7 @@ from . import _lib
 
 
 @torch.no_grad()
+@_lib.device_guarded
 def burgers_numeric_solve_free(u0, f, visc, T, dt=1e-4, num_t=10, mode=None):
     if mode == 'const':
         raise ValueError

@@ -228,6 +228,7 @@ class Unet2D(nn.Module):
 
     # ------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
+    @_lib.device_guarded
     def forward(self, x, time, x_self_cond=None, residual=None):
         """unet.py:387-431.  x: [B,C,H,W] fp32 CUDA, time: [B] -> [B,out_dim,H,W]."""
         _require_cuda(x)

@@ -575,7 +575,8 @@ spatial_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out,
 //      exp(k), two broadcast LDS.128 of v and 8 FMAs.  No cross-warp reduction, 8 accumulators per thread.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-linattn_context_kernel(const float* __restrict__ qkv, float* __restrict__ ctx, int HW, int heads) {
+linattn_context_kernel(const float* __restrict__ qkv, float* __restrict__ ctx, int HW, int heads, float* __restrict__ kstat,
+                       float vscale) {
   constexpr int TP = 64;                       // pixels per tile
   __shared__ __align__(16) float s_k[2][TP][DH];
   __shared__ __align__(16) float s_v[2][TP][DH];
@@ -658,7 +659,11 @@ linattn_context_kernel(const float* __restrict__ qkv, float* __restrict__ ctx, i
   }
   if (warp == 0) s_sum[lane] = ksum;
   __syncthreads();
-  const float inv = 1.0f / s_sum[lane];
+  const float inv = vscale / s_sum[lane];     // vscale: the 2-D variant's v / (h*w) (jf.py:219), 1 for conv3d.py:243-257
+  if (kstat && warp == 0) {                   // softmax_n(k) statistics for the backward pass: [frame*heads + head][d][max, sum]
+    kstat[((size_t)blockIdx.x * DH + lane) * 2 + 0] = s_max[lane];
+    kstat[((size_t)blockIdx.x * DH + lane) * 2 + 1] = s_sum[lane];
+  }
   float* dst = ctx + (size_t)blockIdx.x * DH * DH + lane * DH + warp * 8;   // [d][e]
   *reinterpret_cast<float4*>(dst) = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
   *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
@@ -744,7 +749,8 @@ extern "C" int dpc_temporal_attention(const float* qkv, const float* rope_cos, c
   cudaStream_t st = (cudaStream_t)stream;
   if (F <= 32) {
     const size_t smem = (size_t)4 * 3 * 32 * 36 * sizeof(float);
-    static bool configured = false;
+    static bool configured_[kMaxDevices] = {};
+    bool& configured = configured_[device_ordinal()];
     if (!configured) {
       DPC_CUDA(cudaFuncSetAttribute(temporal_attention_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       DPC_CUDA(cudaFuncSetAttribute(temporal_attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -758,7 +764,8 @@ extern "C" int dpc_temporal_attention(const float* qkv, const float* rope_cos, c
                                                                                HW, heads, use_rope);
   } else {
     const size_t smem = (size_t)4 * 2 * 64 * 36 * sizeof(float);
-    static bool configured = false;
+    static bool configured_[kMaxDevices] = {};
+    bool& configured = configured_[device_ordinal()];
     if (!configured) {
       DPC_CUDA(cudaFuncSetAttribute(temporal_attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = true;
@@ -794,7 +801,20 @@ extern "C" int dpc_spatial_linear_attention(const float* qkv, float* ctx_ws, flo
   using namespace dpc;
   DPC_CHECK_ARG(qkv && ctx_ws && out && BF > 0 && BF <= 65535 && HW > 0 && heads > 0);
   cudaStream_t st = (cudaStream_t)stream;
-  linattn_context_kernel<<<(unsigned)((int64_t)BF * heads), 128, 0, st>>>(qkv, ctx_ws, HW, heads);
+  linattn_context_kernel<<<(unsigned)((int64_t)BF * heads), 128, 0, st>>>(qkv, ctx_ws, HW, heads, nullptr, 1.0f);
+  DPC_LAUNCH_CHECK();
+  dim3 grid((unsigned)((HW + 127) / 128), (unsigned)heads, (unsigned)BF);
+  linattn_apply_kernel<<<grid, 128, 0, st>>>(qkv, ctx_ws, out, HW, heads);
+  DPC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dpc_spatial_linear_attention_ex(const float* qkv, float* ctx_ws, float* kstat, float* out, int32_t BF, int32_t HW,
+                                               int32_t heads, float v_scale, void* stream) {
+  using namespace dpc;
+  DPC_CHECK_ARG(qkv && ctx_ws && out && BF > 0 && BF <= 65535 && HW > 0 && heads > 0 && heads <= 65535);
+  cudaStream_t st = (cudaStream_t)stream;
+  linattn_context_kernel<<<(unsigned)((int64_t)BF * heads), 128, 0, st>>>(qkv, ctx_ws, HW, heads, kstat, v_scale);
   DPC_LAUNCH_CHECK();
   dim3 grid((unsigned)((HW + 127) / 128), (unsigned)heads, (unsigned)BF);
   linattn_apply_kernel<<<grid, 128, 0, st>>>(qkv, ctx_ws, out, HW, heads);

@@ -50,4 +50,22 @@ __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v));
 
 static inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// Per-device launch state.  cudaFuncSetAttribute(MaxDynamicSharedMemorySize) and the SM count belong to ONE device, so every
+// cache of them is indexed by the ordinal of the device that is current at launch time (the binding makes the tensors'
+// device current around every call).
+constexpr int kMaxDevices = 64;
+inline int device_ordinal() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= kMaxDevices) return 0;
+  return d;
+}
+inline int sm_count(int dev) {
+  static int n[kMaxDevices] = {};
+  if (!n[dev]) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess) n[dev] = v;
+  }
+  return n[dev] > 0 ? n[dev] : 1;
+}
+
 }  // namespace dpc

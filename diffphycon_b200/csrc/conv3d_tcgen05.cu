@@ -665,19 +665,16 @@ static int make_w_map(CUtensorMap* m, const float* w, int Kpad, int Npad, int N)
 template <int N, bool PAIR>
 static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMap& a1t, const CUtensorMap& a2t,
                   const CUtensorMap& wm, const CUtensorMap& wm3, const Params& p, size_t smem, cudaStream_t st) {
-  static size_t configured = 0;
+  const int dev = device_ordinal();
+  static size_t configured_[kMaxDevices] = {};
+  size_t& configured = configured_[dev];
   if (smem > configured) {
     DPC_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<N, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (PAIR) DPC_CUDA(cudaFuncSetAttribute(conv3d_tc_kernel<N, PAIR>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0));
     configured = smem;
   }
   const size_t ntiles = (size_t)p.B * (p.quad ? p.F / p.quad : p.F) * p.tiles_f;
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    DPC_CUDA(cudaGetDevice(&dev));
-    DPC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int num_sms = sm_count(dev);
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(NTHREADS_TC);
   cfg.dynamicSmemBytes = smem;
@@ -691,8 +688,10 @@ static int launch(const CUtensorMap& a1, const CUtensorMap& a2, const CUtensorMa
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     // persistent CTA pairs: as many clusters as can be co-resident (an SM pair of one TPC each)
-    static int max_clusters = 0;
-    static size_t clusters_smem = 0;
+    static int max_clusters_[kMaxDevices] = {};
+    static size_t clusters_smem_[kMaxDevices] = {};
+    int& max_clusters = max_clusters_[dev];
+    size_t& clusters_smem = clusters_smem_[dev];
     if (!max_clusters || smem > clusters_smem) {
       cfg.gridDim = dim3((unsigned)(num_sms & ~1));
       int n = 0;

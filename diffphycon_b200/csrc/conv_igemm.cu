@@ -323,7 +323,8 @@ static int launch(const dpc_conv_params& p, int M, int K, cudaStream_t st) {
   const int tilesN = p.Npad / BN;
   const int tilesM = (M + BM - 1) / BM;
   const size_t smem = (size_t)STAGES * (BM + BN) * LDS_ * sizeof(float);
-  static bool configured = false;
+  static bool configured_[kMaxDevices] = {};
+  bool& configured = configured_[device_ordinal()];
   if (!configured) {
     DPC_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<BN, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;

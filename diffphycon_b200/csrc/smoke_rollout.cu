@@ -398,7 +398,8 @@ extern "C" int dpc_smoke_rollout(const int8_t* fluid_mask, const float* velocity
   a.velocitys = velocitys; a.smoke_out = smoke_out; a.iterations = iterations;
   a.nt = nt; a.nx = nx; a.T = T; a.dt = dt; a.accuracy = accuracy; a.max_iterations = max_iterations;
   const size_t smem = (size_t)(NC + 1 + 4 * 32 * 9) * sizeof(double);
-  static bool configured = false;
+  static bool configured_[kMaxDevices] = {};
+  bool& configured = configured_[device_ordinal()];
   if (!configured) {
     DPC_CUDA(cudaFuncSetAttribute(smoke_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;

@@ -538,18 +538,15 @@ extern "C" int dpc_spatial_linear_block_fused(const float* x, const float* w_qkv
   if (rc) return rc;
   rc = make_map_2d(&mm, mt_ws, HID, (int64_t)BF * sl::C, 32, 64);
   if (rc) return rc;
-  static bool configured = false;
+  const int dev = device_ordinal();
+  static bool configured_[kMaxDevices] = {};
+  bool& configured = configured_[dev];
   if (!configured) {
     DPC_CUDA(cudaFuncSetAttribute(linattn_context_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM));
     DPC_CUDA(cudaFuncSetAttribute(linattn_apply_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B_SMEM));
     configured = true;
   }
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    DPC_CUDA(cudaGetDevice(&dev));
-    DPC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int num_sms = sm_count(dev);
   CtxParams pa{ctx_ws, eps, BF, HW};
   linattn_context_tc_kernel<<<(unsigned)(BF < num_sms ? BF : num_sms), THREADS, A_SMEM, st>>>(mx, mwkv, pa);
   DPC_LAUNCH_CHECK();

@@ -272,17 +272,14 @@ extern "C" int dpc_stem_conv_tcgen05(const float* x, const float* w, const float
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_err(-1, "cuTensorMapEncodeTiled(stem weights) failed", __FILE__, (int)r);
   }
-  static size_t configured = 0;
+  const int dev = device_ordinal();
+  static size_t configured_[kMaxDevices] = {};
+  size_t& configured = configured_[dev];
   if (smem > configured) {
     DPC_CUDA(cudaFuncSetAttribute(stem_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = smem;
   }
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    DPC_CUDA(cudaGetDevice(&dev));
-    DPC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int num_sms = sm_count(dev);
   const size_t ntiles = (size_t)B * F * p.tiles_f;
   const unsigned grid = (unsigned)(ntiles < (size_t)num_sms ? ntiles : (size_t)num_sms);
   stem_conv_tc_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(ta, tw, p);

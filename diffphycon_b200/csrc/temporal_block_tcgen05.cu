@@ -427,17 +427,14 @@ extern "C" int dpc_temporal_block_fused(const float* x, const float* w_qkv, cons
   if (rc) return rc;
   rc = make_w_map(&mo, w_out, HID, tb::C, 64);
   if (rc) return rc;
-  static bool configured = false;
+  const int dev = device_ordinal();
+  static bool configured_[kMaxDevices] = {};
+  bool& configured = configured_[dev];
   if (!configured) {
     DPC_CUDA(cudaFuncSetAttribute(temporal_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     configured = true;
   }
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    DPC_CUDA(cudaGetDevice(&dev));
-    DPC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int num_sms = sm_count(dev);
   Params p{rope_cos, rope_sin, pos_bias, eps, B, HW};
   const int ntiles = B * (HW / 4);
   const unsigned grid = (unsigned)(ntiles < num_sms ? ntiles : num_sms);

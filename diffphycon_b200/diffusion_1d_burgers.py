@@ -184,6 +184,7 @@ class GaussianDiffusion(nn.Module):
         return float(torch.as_tensor(v, dtype=torch.float64).to(torch.float32))
 
     # ---- burgers.py:396-450 -----------------------------------------------------------------------------------
+    @_lib.device_guarded
     def model_predictions(self, x, t, x_self_cond=None, residual=None, clip_x_start=False, rederive_pred_noise=False, **kwargs):
         """Returns (pred_noise, x_start) like the reference; `t` is the batched time tensor, all entries equal."""
         ti = int(t[0].item()) if torch.is_tensor(t) else int(t)
@@ -254,6 +255,7 @@ class GaussianDiffusion(nn.Module):
         return pred_noise, x_start, pred
 
     # ---- burgers.py:464-470 -----------------------------------------------------------------------------------
+    @_lib.device_guarded
     def p_sample(self, x, t: int, x_self_cond=None, residual=None, **kwargs):
         x = x.contiguous()
         noise = self.sample_noise(x.shape, x.device) if t > 0 else None

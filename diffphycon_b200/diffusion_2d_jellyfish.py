@@ -217,14 +217,15 @@ class GaussianDiffusion(nn.Module):
     @torch.no_grad()
     def p_sample_loop(self, shape, design_fn=None, design_guidance="standard", return_all_timesteps=None, cond=None,
                       thetas_0=None, bd_updater=None, device=None):
-        st = self._begin(shape, cond, thetas_0, bd_updater)
-        steps = reversed(range(0, self.num_timesteps))
-        if self.progress:
-            from tqdm.auto import tqdm
-            steps = tqdm(steps, desc='sampling loop time step', total=self.num_timesteps)
-        for t in steps:
-            self._ddpm_step(st, t, design_fn, design_guidance)
-        return [st.x[:, :, :3], st.theta_mean.clone()]
+        with _lib.on_device(self.betas.device):
+            st = self._begin(shape, cond, thetas_0, bd_updater)
+            steps = reversed(range(0, self.num_timesteps))
+            if self.progress:
+                from tqdm.auto import tqdm
+                steps = tqdm(steps, desc='sampling loop time step', total=self.num_timesteps)
+            for t in steps:
+                self._ddpm_step(st, t, design_fn, design_guidance)
+            return [st.x[:, :, :3], st.theta_mean.clone()]
 
     # ---- DDIM (jf.py:883-966) -----------------------------------------------------------------------------------------
     @torch.no_grad()
@@ -233,29 +234,30 @@ class GaussianDiffusion(nn.Module):
         if return_all_timesteps:
             raise NotImplementedError("return_all_timesteps stacks tensors with lists in the reference (jf.py:964) and fails")
         assert design_fn is not None, "the DDIM path calls design_fn unconditionally (jf.py:735)"
-        eta = self.ddim_sampling_eta
-        times = torch.linspace(-1, self.num_timesteps - 1, steps=self.sampling_timesteps + 1)
-        times = list(reversed(times.int().tolist()))
-        pairs = list(zip(times[:-1], times[1:]))
-        st = self._begin(shape, cond, thetas_0, bd_updater)
-        s = self._sched()
-        if self.progress:
-            from tqdm.auto import tqdm
-            pairs = tqdm(pairs, desc='sampling loop time step')
-        for time, time_next in pairs:
-            if time_next < 0:
-                continue    # the reference evaluates the models once more but returns the previous pair's result
-            eps_j, eps_w = self._eps(st, time)
-            _lib.jelly_x_start(st.x, eps_j, st.x_start, float(s['sqrt_recip_alphas_cumprod'][time]),
-                               float(s['sqrt_recipm1_alphas_cumprod'][time]), False)
-            g = self._design_gradient(design_fn, st.x_start, st.bd_0_expand)
-            ga, gb = self._guidance_scalars(time, design_guidance, ddim=True)
-            alpha, alpha_next = s['alphas_cumprod'][time], s['alphas_cumprod'][time_next]
-            sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
-            c = (1 - alpha_next - sigma ** 2).sqrt()
-            noise = self.sample_noise(st.x_start.shape, st.x.device)
-            self._finish_step(st, eps_j, eps_w, g, noise, ga, gb, float(alpha_next.sqrt()), float(c), float(sigma), True)
-        return [st.x[:, :, :3], st.theta_mean.clone()]
+        with _lib.on_device(self.betas.device):
+            eta = self.ddim_sampling_eta
+            times = torch.linspace(-1, self.num_timesteps - 1, steps=self.sampling_timesteps + 1)
+            times = list(reversed(times.int().tolist()))
+            pairs = list(zip(times[:-1], times[1:]))
+            st = self._begin(shape, cond, thetas_0, bd_updater)
+            s = self._sched()
+            if self.progress:
+                from tqdm.auto import tqdm
+                pairs = tqdm(pairs, desc='sampling loop time step')
+            for time, time_next in pairs:
+                if time_next < 0:
+                    continue    # the reference evaluates the models once more but returns the previous pair's result
+                eps_j, eps_w = self._eps(st, time)
+                _lib.jelly_x_start(st.x, eps_j, st.x_start, float(s['sqrt_recip_alphas_cumprod'][time]),
+                                   float(s['sqrt_recipm1_alphas_cumprod'][time]), False)
+                g = self._design_gradient(design_fn, st.x_start, st.bd_0_expand)
+                ga, gb = self._guidance_scalars(time, design_guidance, ddim=True)
+                alpha, alpha_next = s['alphas_cumprod'][time], s['alphas_cumprod'][time_next]
+                sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+                c = (1 - alpha_next - sigma ** 2).sqrt()
+                noise = self.sample_noise(st.x_start.shape, st.x.device)
+                self._finish_step(st, eps_j, eps_w, g, noise, ga, gb, float(alpha_next.sqrt()), float(c), float(sigma), True)
+            return [st.x[:, :, :3], st.theta_mean.clone()]
 
     @torch.no_grad()
     def sample(self, batch_size=16, design_fn=None, design_guidance="standard", return_all_timesteps=False, cond=None,

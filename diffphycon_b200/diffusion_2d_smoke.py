@@ -197,6 +197,7 @@ class GaussianDiffusion(nn.Module):
 
     # ---- DDPM -----------------------------------------------------------------------------------------------------
     @torch.no_grad()
+    @_lib.device_guarded
     def p_sample(self, shape, x, t: int, x_self_cond=None, clip_denoised=True, design_fn=None,
                  design_guidance="standard", low=None, init=None, init_u=None, _impose_init=False):
         """smoke.py:671-699.  Returns (x_{t-1}, x_start)."""
@@ -262,6 +263,7 @@ class GaussianDiffusion(nn.Module):
         return img
 
     @torch.no_grad()
+    @_lib.device_guarded
     def ddim_step(self, img, time: int, time_next: int, design_fn=None, design_guidance="standard", init=None,
                   init_u=None, low=None, noise=None):
         """One iteration of the DDIM loop, smoke.py:739-775 (model_predictions with clip_x_start=True,

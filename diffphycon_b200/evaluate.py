@@ -13,6 +13,7 @@ from . import smoke_rollout as sr
 
 
 @torch.no_grad()
+@_lib.device_guarded
 def multi_evaluate(pred: torch.Tensor, data: torch.Tensor, w_energy: float = 0.0, per_timelength: int = 256,
                    mask_window=(8, 56), sim=None):
     """pred [B,F,6,S,S] sampled (rescaled) trajectories, data [B,T,6,Sd,Sd] the test item the initial density comes from

@@ -72,6 +72,7 @@ def init_velocity_() -> np.ndarray:
 
 
 @torch.no_grad()
+@_lib.device_guarded
 def solver_batch(sim: SmokeSimulation, init_velocity, init_density, c1, c2, per_timelength: int, dt: float = 1.0,
                  accuracy: float = 1e-8, max_iterations: int = 500):
     """Batched rollout on the device.  init_velocity [B,128,128,2] (or [128,128,2] / [1,128,128,2] shared),

@@ -387,6 +387,7 @@ class Unet3D_with_Conv3D(nn.Module):
     # forward
     # ------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
+    @_lib.device_guarded
     def forward(self, x, time, cond=None, null_cond_prob=0., focus_present_mask=None, prob_focus_present=0.):
         """conv3d.py:486-552.  x: [B,F,C,H,W] fp32 CUDA, time: [B] -> [B,F,out_dim,H,W]."""
         _require_cuda(x)
@@ -409,6 +410,7 @@ class Unet3D_with_Conv3D(nn.Module):
         return out
 
     @torch.no_grad()
+    @_lib.device_guarded
     def forward_slice(self, x_full, c0, time, out):
         """Same as forward but reads channels [c0, c0+self.channels) of a wider reference-layout tensor without
         materialising the slice (replaces x[:, :, 3:5] at smoke.py:612) and writes into a caller-provided `out`."""

@@ -289,6 +289,51 @@ int dpc_jelly_write_bd(const float* pred_bd, const float* bd_0, float* x_next, f
 int dpc_burgers_rollout(const float* u0, const float* f, float* traj, int32_t N, int32_t s, int32_t Nt, int32_t steps,
                         float t0, float t1, float d0, float d1, float d2, float dt, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Jellyfish surrogate networks: the 2-D `Unet` boundary updater and `ForceUnet`
+ * (diffusion/diffusion_2d_jellyfish.py:276-403, :406-481; cited as jf.py) forward and BACKWARD w.r.t. activations and the
+ * time conditioning — what `force_fn` (inference/inference_2d_jellyfish.py:85-114) obtains through torch.autograd.grad.
+ * Tensors are channels-last fp32 [N images][HW][C].  The dgrad convolutions are dpc_conv_igemm / dpc_conv3d_tcgen05 calls
+ * with transposed, spatially flipped packed weights; the entry points below are everything else.
+ * ------------------------------------------------------------------------------------------------------- */
+/* LinearAttention forward (jf.py:206-225): like dpc_spatial_linear_attention with v scaled by v_scale (= 1/(h*w), jf.py:219)
+ * and, if kstat != NULL, the softmax_n(k) statistics [BF*heads][32][2] = (max, sum) kept for the backward pass. */
+int dpc_spatial_linear_attention_ex(const float* qkv, float* ctx_ws, float* kstat, float* out, int32_t BF, int32_t HW,
+                                    int32_t heads, float v_scale, void* stream);
+/* LinearAttention core backward: qkv [BF*HW][3*heads*32], ctx [BF*heads][32][32] and kstat from the forward, dout
+ * [BF*HW][heads*32] -> dqkv (same layout as qkv); dctx_ws: BF*heads*32*32 floats; scale = 32^-0.5. */
+int dpc_linattn2d_bwd(const float* qkv, const float* ctx, const float* kstat, const float* dout, float* dctx_ws, float* dqkv,
+                      int32_t BF, int32_t HW, int32_t heads, float scale, float v_scale, void* stream);
+/* softmax Attention core backward (jf.py:241-255): out = the forward's attention output [BF*HW][heads*32]; returns -2 when
+ * HW exceeds what one CTA's shared memory holds (~780 tokens). */
+int dpc_attention2d_bwd(const float* qkv, const float* out, const float* dout, float* dqkv, int32_t BF, int32_t HW,
+                        int32_t heads, float scale, void* stream);
+/* Backward of dpc_groupnorm_silu (Block.forward after proj, jf.py:196-204) w.r.t. the raw conv output y:
+ * dy [B][rows][C]; dss (nullable, same layout / stride / offset as scale_shift) receives d scale and d shift per (sample,
+ * channel); sums_ws: B*C*2 doubles. */
+int dpc_gn_silu_bwd(const float* y, const double* stats, const float* gamma, const float* beta, const float* scale_shift,
+                    int64_t ss_stride, int64_t ss_off, const float* dout, float* dy, double* sums_ws, float* dss, int32_t B,
+                    int64_t rows_per_sample, int32_t C, int32_t groups, float eps, void* stream);
+/* Backward of dpc_layernorm_channels w.r.t. x: dx = LN'(x; gamma) dy (+ add, nullable: the residual branch's gradient). */
+int dpc_layernorm_channels_bwd(const float* x, const float* gamma, const float* dy, const float* add, float* dx, int64_t rows,
+                               int32_t C, float eps, int32_t use_rsqrt, void* stream);
+/* out = a + b (n % 4 == 0; out may alias a or b). */
+int dpc_add(const float* a, const float* b, float* out, int64_t n, void* stream);
+/* Backward of dpc_upsample_nearest2x: dy [N,2H,2W,C] -> dx [N,H,W,C] (sum of each 2x2 block). */
+int dpc_sumpool2x2(const float* dy, float* dx, int64_t N, int32_t H, int32_t W, int32_t C, void* stream);
+/* ForceUnet head (jf.py:478-479): out[n][o] = bias[o] + sum_c W[o][c] * mean_hw x[n][:][c], and its backward w.r.t. x. */
+int dpc_mean_head(const float* x, const float* W, const float* bias, float* out, int64_t N, int32_t HW, int32_t C, int32_t O,
+                  void* stream);
+int dpc_mean_head_bwd(const float* dout, const float* W, float* dx, int64_t N, int32_t HW, int32_t C, int32_t O, void* stream);
+/* time_mlp with a FLOAT time (the boundary updater is conditioned on theta, jf.py:313-318, inference_2d_jellyfish.py:99-102):
+ * same as dpc_time_embed otherwise. */
+int dpc_time_embed_f32(const float* t, const float* freqs, const float* w1, const float* b1, const float* w2, const float* b2,
+                       float* hidden_ws, float* t_emb, int32_t B, int32_t dim, void* stream);
+/* d(sum over all ResnetBlock scale/shift rows)/d t: backward through dpc_time_proj (w_proj [total][4*dim]), SiLU, time_mlp and
+ * the sinusoidal embedding, given dss [B][total] and the forward's t_emb [B][4*dim] -> dt [B]. */
+int dpc_time_mlp_bwd(const float* t, const float* freqs, const float* w1, const float* b1, const float* w2, const float* w_proj,
+                     const float* t_emb, const float* dss, float* dt, int32_t B, int32_t dim, int32_t total, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -360,8 +360,115 @@ def jelly_write_bd(pred_bd, bd_0, x_next, x_w, cond_steps):
     x_w[:, :, 3:6] = bd
 
 
+
+# ---- jellyfish surrogate networks (csrc/nets2d.cu): forward variants and BACKWARD kernels, emulated with torch.autograd ----
+def spatial_linear_attention_ex(qkv, ctx_ws, kstat, out, BF, HW, heads, v_scale):
+    hid = heads * HEADS_DIM
+    t = qkv[: BF * HW * 3 * hid].reshape(BF, HW, 3 * hid)
+    q, k, v = _split_heads(t, heads)  # b h n d
+    qs = q.softmax(dim=-1) * (HEADS_DIM ** -0.5)
+    kmax = k.max(dim=-2).values
+    ksum = (k - kmax[:, :, None, :]).exp().sum(dim=-2)
+    ks = k.softmax(dim=-2)
+    ctx = torch.einsum("bhnd,bhne->bhde", ks, v * v_scale)
+    o = torch.einsum("bhde,bhnd->bhne", ctx, qs).transpose(1, 2).reshape(BF, HW, hid)
+    out[: o.numel()] = o.reshape(-1)
+    ctx_ws[: ctx.numel()] = ctx.reshape(-1)
+    if kstat is not None:
+        kstat[: BF * heads * HEADS_DIM * 2] = torch.stack([kmax, ksum], dim=-1).reshape(-1)
+
+
+def linattn2d_bwd(qkv, ctx, kstat, dout, dctx_ws, dqkv, BF, HW, heads, v_scale):
+    hid = heads * HEADS_DIM
+    with torch.enable_grad():
+        t = qkv[: BF * HW * 3 * hid].reshape(BF, HW, 3 * hid).clone().requires_grad_()
+        q, k, v = _split_heads(t, heads)
+        qs = q.softmax(dim=-1) * (HEADS_DIM ** -0.5)
+        ks = k.softmax(dim=-2)
+        c = torch.einsum("bhnd,bhne->bhde", ks, v * v_scale)
+        o = torch.einsum("bhde,bhnd->bhne", c, qs).transpose(1, 2).reshape(BF, HW, hid)
+        (g,) = torch.autograd.grad(o, t, dout[: BF * HW * hid].reshape(BF, HW, hid))
+    dqkv[: g.numel()] = g.reshape(-1)
+
+
+def attention2d_bwd(qkv, out, dout, dqkv, BF, HW, heads):
+    hid = heads * HEADS_DIM
+    with torch.enable_grad():
+        t = qkv[: BF * HW * 3 * hid].reshape(BF, HW, 3 * hid).clone().requires_grad_()
+        q, k, v = _split_heads(t, heads)
+        sim = torch.einsum("bhid,bhjd->bhij", q * (HEADS_DIM ** -0.5), k)
+        o = torch.einsum("bhij,bhjd->bhid", sim.softmax(-1), v).transpose(1, 2).reshape(BF, HW, hid)
+        (g,) = torch.autograd.grad(o, t, dout[: BF * HW * hid].reshape(BF, HW, hid))
+    dqkv[: g.numel()] = g.reshape(-1)
+
+
+def gn_silu_bwd(y, stats, gamma, beta, scale_shift, ss_stride, ss_off, dout, dy, sums_ws, dss, B, rps, Cn, groups, eps=1e-5):
+    with torch.enable_grad():
+        v = y[: B * rps * Cn].reshape(B, rps, Cn).clone().requires_grad_()
+        t = torch.nn.functional.group_norm(v.permute(0, 2, 1), groups, gamma, beta, eps=eps).permute(0, 2, 1)
+        ins = [v]
+        if scale_shift is not None:
+            ss = scale_shift[: B * ss_stride].reshape(B, ss_stride).clone().requires_grad_()
+            t = t * (ss[:, None, ss_off:ss_off + Cn] + 1) + ss[:, None, ss_off + Cn:ss_off + 2 * Cn]
+            ins.append(ss)
+        o = torch.nn.functional.silu(t)
+        gs = torch.autograd.grad(o, ins, dout[: B * rps * Cn].reshape(B, rps, Cn))
+    dy[: B * rps * Cn] = gs[0].reshape(-1)
+    if dss is not None:
+        d = dss[: B * ss_stride].reshape(B, ss_stride)
+        d[:, ss_off:ss_off + 2 * Cn] = gs[1][:, ss_off:ss_off + 2 * Cn]
+
+
+def layernorm_channels_bwd(x, gamma, dy, add, dx, rows, Cn, eps=1e-5, use_rsqrt=True):
+    with torch.enable_grad():
+        v = x[: rows * Cn].reshape(rows, Cn).clone().requires_grad_()
+        mean = v.mean(dim=1, keepdim=True)
+        var = v.var(dim=1, unbiased=False, keepdim=True)
+        o = (v - mean) * (var + eps).rsqrt() * gamma
+        (g,) = torch.autograd.grad(o, v, dy[: rows * Cn].reshape(rows, Cn))
+    if add is not None:
+        g = g + add[: rows * Cn].reshape(rows, Cn)
+    dx[: rows * Cn] = g.reshape(-1)
+
+
+def add(a, b, out, n):
+    out[:n] = a[:n] + b[:n]
+
+
+def sumpool2x2(dy, dx, N, H, W, Cn):
+    v = dy[: N * 4 * H * W * Cn].reshape(N, H, 2, W, 2, Cn).sum((2, 4))
+    dx[: v.numel()] = v.reshape(-1)
+
+
+def mean_head(x, W, bias, out, N, HW, Cn, O):
+    v = x[: N * HW * Cn].reshape(N, HW, Cn).mean(1)
+    out.copy_(v @ W.t() + bias)
+
+
+def mean_head_bwd(dout, W, dx, N, HW, Cn, O):
+    g = ((dout @ W) / HW)[:, None, :].expand(N, HW, Cn)
+    dx[: N * HW * Cn] = g.reshape(-1)
+
+
+def time_embed_f32(t, freqs, w1, b1, w2, b2, hidden_ws, t_emb, B, dim):
+    time_embed(t, freqs, w1, b1, w2, b2, hidden_ws, t_emb, B, dim)
+
+
+def time_mlp_bwd(t, freqs, w1, b1, w2, w_proj, t_emb, dss, dt, B, dim, total):
+    with torch.enable_grad():
+        tr = t.clone().requires_grad_()
+        arg = tr[:, None] * freqs[None, :]
+        emb = torch.cat((arg.sin(), arg.cos()), dim=-1)
+        te = torch.nn.functional.gelu(emb @ w1.t() + b1) @ w2.t()
+        ss = torch.nn.functional.silu(te + (t_emb[: B * dim * 4].reshape(B, dim * 4) - te).detach()) @ w_proj.t()
+        (g,) = torch.autograd.grad(ss, tr, dss[: B * total].reshape(B, total))
+    dt.copy_(g)
+
+
 EMULATED = ("temporal_block_fused", "gn_fold", "final_proj", "spatial_linear_block_fused", "stem_conv", "jelly_x_start", "jelly_step", "jelly_write_bd", "burgers_model_output", "ddpm_posterior_step", "conv", "groupnorm_silu", "layernorm_channels", "pack_input", "temporal_attention", "spatial_attention",
-            "spatial_linear_attention", "time_embed", "time_proj", "predict_x_start", "guided_step", "upsample_nearest2x")
+            "spatial_linear_attention", "time_embed", "time_proj", "predict_x_start", "guided_step", "upsample_nearest2x",
+            "spatial_linear_attention_ex", "linattn2d_bwd", "attention2d_bwd", "gn_silu_bwd", "layernorm_channels_bwd", "add", "sumpool2x2",
+            "mean_head", "mean_head_bwd", "time_embed_f32", "time_mlp_bwd")
 
 
 def install_raw():
