@@ -56,6 +56,8 @@ struct Params {
                               // input frame feeds are stacked into one MMA of N = 64 / 128 / 192 (see the MMA issuer)
   int staged;                 // conv epilogue: stores staged through shared memory (128-byte row segments)
   int dbg;                    // DPC_TC_DEBUG experiment switches (1: weight boxes fetched once, 2: A boxes fetched once)
+  int nkt, ptt;               // temporal taps / temporal padding: 3, 1 for the 3x3x3 conv; 1, 0 for a 3x3 conv over images (F = 1)
+  int gcols;                  // GroupNorm: channels per group of the WHOLE layer (Cout / 8); a launch may cover a column slice
 };
 
 // cta_group::2 helpers (PAIR mode): the two CTAs of a cluster run one M = 256 MMA per instruction.  Each CTA keeps its own A
@@ -146,7 +148,7 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
   const int nch = Cin / KCH, nch1 = p.C1 / KCH;
   const bool quad = PAIR && p.quad;
   const int Q = quad ? p.quad : 1;                      // output frames per tile
-  const int nblk = quad ? (Q + 2) * nch : p.mode == 1 ? 4 * nch : p.mode == 2 ? nch : p.gemm ? nch : 3 * nch * p.ndw;   // A boxes per tile
+  const int nblk = quad ? (Q + 2) * nch : p.mode == 1 ? 4 * nch : p.mode == 2 ? nch : p.gemm ? nch : p.nkt * nch * p.ndw;   // A boxes per tile
   const int ntap = p.mode ? 4 : p.gemm ? p.ncol : 9 / p.ndw;                                       // weight boxes per A box
   const int AB = p.AB;                                   // TMEM accumulator sets (2 = epilogue overlaps the next tile)
   const int Fd = quad ? p.F / Q : p.F;                  // frames (or frame quads) per sample in the tile enumeration
@@ -255,8 +257,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           const CUtensorMap* mp = (r0 + rows_part <= p.R) ? (src1 ? &tmA1 : &tmA2) : (src1 ? &tmA1t : &tmA2t);
           const uint32_t dst = a_buf + sa * p.a_bytes + (uint32_t)(r0 * p.pitch * ROW_BYTES);
           if (p.mode) tma_load_5d(dst, mp, fullA + 8 * sa, c0, w0, h0 + (p.mode == 1 ? 2 * r0 : r0), f, b);
-          else if (PAIR) tma_load_5d_pair(dst, mp, fullA_l + 8 * sa, c0, dwb - 1, hq - halo + r0, f + dt - 1, b);
-          else tma_load_5d(dst, mp, fullA + 8 * sa, c0, dwb - 1, hq - halo + r0, f + dt - 1, b);
+          else if (PAIR) tma_load_5d_pair(dst, mp, fullA_l + 8 * sa, c0, dwb - 1, hq - halo + r0, f + dt - p.ptt, b);
+          else tma_load_5d(dst, mp, fullA + 8 * sa, c0, dwb - 1, hq - halo + r0, f + dt - p.ptt, b);
         }
         if (++sa == NA) { sa = 0; pha ^= 1; }
       }
@@ -619,7 +621,8 @@ conv3d_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant
           const int slot = et;   // after the halving lane L holds value index L >> 1 (bit k of L selects bit k-1)
           const double tot = ((s_part[0][et] + s_part[1][et]) + (s_part[2][et] + s_part[3][et])) +
                              ((s_part[4][et] + s_part[5][et]) + (s_part[6][et] + s_part[7][et]));
-          const int which = slot >> 3, grp = slot & 7;
+          // local slot = 32/GPC... columns [grp*N/8, (grp+1)*N/8) of this launch's column slice -> group of the whole layer
+          const int which = slot >> 3, grp = (p.wrow0 + (slot & 7) * (N / 8)) / p.gcols;
           atomicAdd(p.gn_stats + ((size_t)b * 8 + grp) * 2 + which, tot);
         }
       }
@@ -725,8 +728,11 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
                          c.ow_mul == 1 && c.Hfull == H && c.Wfull == W && c.out_layout == 0 && c.precise == 0 &&
                          c.C1 % KCH == 0 && c.C2 % KCH == 0 && c.C1 > 0 && W >= 4 && W + 2 <= 256 && H >= 1 &&
                          c.Kpad == c.ntaps * (c.C1 + c.C2);
-  const bool conv_ok = common_ok && c.ntaps == 27 && c.pt == 1 && c.ph == 1 && c.pw == 1 && c.residual == nullptr &&
-                       (c.Cout == 64 || c.Cout == 128 || c.Cout == 256) && c.Npad == c.Cout;
+  // 3x3x3 over frames (pt = 1) or 3x3 over images (ntaps = 9, pt = 0: the 2-D networks of diffusion_2d_jellyfish.py:189-204);
+  // Cout = 512 runs as two 256-column launches
+  const bool conv_ok = common_ok && ((c.ntaps == 27 && c.pt == 1) || (c.ntaps == 9 && c.pt == 0)) && c.ph == 1 && c.pw == 1 &&
+                       c.residual == nullptr && (c.Cout == 64 || c.Cout == 128 || c.Cout == 256 || c.Cout == 512) &&
+                       c.Npad == c.Cout;
   // 1x1x1 conv / Linear: N tiles of 64 / 128 / 256 columns (e.g. the 384-wide qkv projection = 3 x 128)
   const bool gemm_ok = common_ok && c.ntaps == 1 && c.pt == 0 && c.ph == 0 && c.pw == 0 && c.gn_stats == nullptr &&
                        (c.Cout == 64 || c.Cout % 128 == 0) && c.Npad >= c.Cout;
@@ -749,12 +755,15 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   // cta_group::2 pairs (two consecutive frames per cluster) for the 3x3x3 convolutions; DPC_TC_PAIR=0 disables
   const char* pair_env = getenv("DPC_TC_PAIR");          // read per call: the tests run every shape both ways
   const bool pair = !gemm && mode == 0 && !(pair_env && atoi(pair_env) == 0) && ((int64_t)c.B * F) % 2 == 0;
-  const int Ntile = gemm ? (c.Cout == 64 ? 64 : (c.Cout == 256 ? 256 : 128)) : c.Cout;
+  const int Ntile = gemm ? (c.Cout == 64 ? 64 : (c.Cout == 256 ? 256 : 128)) : (c.Cout > 256 ? 256 : c.Cout);
   Params p;
   p.bias = c.bias; p.residual = c.residual; p.res_scale = c.res_scale; p.res_shift = c.res_shift; p.y = c.y; p.gn_stats = c.gn_stats; p.gn_groups = c.gn_groups;
   p.B = c.B; p.F = F; p.H = mode == 1 ? c.Ho : H; p.W = mode == 1 ? c.Wo : W; p.C1 = c.C1; p.C2 = c.C2; p.Cout = c.Cout;
   p.mode = mode; p.cls_h = c.oh_off; p.cls_w = c.ow_off; p.Hout = c.Hfull; p.Wout = c.Wfull; p.o_mul = c.oh_mul;
   p.gemm = gemm ? 1 : 0;
+  p.nkt = (conv_ok && c.ntaps == 9) ? 1 : 3;
+  p.ptt = (conv_ok && c.ntaps == 9) ? 0 : 1;
+  p.gcols = c.Cout / 8;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("DPC_TC_DEBUG"); dbg = e ? atoi(e) : 0; } p.dbg = dbg; }
   p.ldy = c.Cout;
   p.wrow0 = 0;
@@ -770,7 +779,7 @@ extern "C" int dpc_conv3d_tcgen05(const dpc_conv_params* pp, void* stream) {
   const char* quad_env = getenv("DPC_TC_QUAD");
   const int Qreq = quad_env ? atoi(quad_env) : 0;      // 1 or 4: four frames per tile; 2: two frames per tile
   const int Qn = Qreq == 2 ? 2 : 4;
-  const bool quad = pair && c.Cout == 64 && p.ndw == 1 && F % Qn == 0 && ((int64_t)c.B * (F / Qn)) % 2 == 0 &&
+  const bool quad = pair && p.nkt == 3 && c.Cout == 64 && p.ndw == 1 && F % Qn == 0 && ((int64_t)c.B * (F / Qn)) % 2 == 0 &&
                     (Qreq == 1 || Qreq == 2 || Qreq == 4);
   p.quad = quad ? Qn : 0;
   // gemm: up to 512 accumulator columns = ncol column tiles side by side, so A is read once for (up to) 512 outputs

@@ -83,7 +83,10 @@ int dpc_conv_igemm(const dpc_conv_params* p, void* stream);
  * Same arguments, weight packing and epilogue as dpc_conv_igemm (bias, residual for 1x1x1, GroupNorm(8) partial statistics
  * for 3x3x3).
  * Supported: channels-last output, C1 % 32 == 0, C2 % 32 == 0, 4 <= W <= 254, precise == 0, and
- *   ntaps == 27: unit stride, pad 1, no residual, Cout in {64,128,256} == Npad, gn_groups in {0, 8};
+ *   ntaps == 27: unit stride, pad 1, no residual, Cout in {64,128,256,512} == Npad (512 = two 256-column launches),
+ *                gn_groups in {0, 8};
+ *   ntaps == 9 : the same kernel for 3x3 convolutions over IMAGES (Fi = Fo = 1, pt = 0, ph = pw = 1) — the 2-D networks of
+ *                diffusion/diffusion_2d_jellyfish.py:189-204 and their dgrad convolutions;
  *   ntaps == 1 : unit stride, pad 0, no gn_stats, Cout == 64 or Cout % 128 == 0 (column tiles of 64/128/256, up to 512
  *                outputs per pass over the input);
  *   ntaps == 16: kernel 1x4x4, stride (1,2,2), pad (0,1,1), C2 == 0, Cout in {64,128,256} == Npad, no residual / gn_stats;

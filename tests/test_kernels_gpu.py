@@ -645,3 +645,37 @@ def test_temporal_block_fused_declines_other_shapes():
     z = torch.zeros(16, device="cuda")
     assert _lib.temporal_block_fused(z, z, z, z, z, z, z, 1, 16, 4, 64, 4) is False
     assert _lib.temporal_block_fused(z, z, z, z, z, z, z, 1, 32, 4, 128, 4) is False
+
+
+TC_2D_CASES = [
+    # name, N images, H, W, C1, C2, Cout   (3x3 convs of the jellyfish 2-D networks, diffusion_2d_jellyfish.py:189-204)
+    ("img64_c64", 4, 64, 64, 64, 0, 64),
+    ("img128_c64", 2, 128, 128, 64, 0, 64),
+    ("img32_c128", 6, 32, 32, 128, 0, 128),
+    ("img16_c256_to_512", 4, 16, 16, 256, 0, 512),       # Cout = 512: two 256-column launches, GroupNorm groups span both
+    ("img8_c512", 6, 8, 8, 512, 0, 512),
+    ("img16_concat_1024_to_512", 2, 16, 16, 512, 512, 512),
+    ("img64_concat_128_to_64", 2, 64, 64, 64, 64, 64),
+    ("odd_batch_c128", 3, 32, 32, 128, 0, 64),           # N odd: single-CTA mode
+]
+
+
+@pytest.mark.parametrize("case", TC_2D_CASES, ids=[c[0] for c in TC_2D_CASES])
+def test_conv2d_3x3_tcgen05(case):
+    """kt = 1 mode of dpc_conv3d_tcgen05 (ntaps = 9, images as single-frame samples) against fp64, with GroupNorm statistics."""
+    _, N, H, W, C1, C2, Cout = case
+    gen = g(17)
+    x1 = torch.randn(N, 1, H, W, C1, generator=gen)
+    x2 = torch.randn(N, 1, H, W, C2, generator=gen) if C2 else None
+    w = torch.randn(Cout, C1 + C2, 3, 3, generator=gen) / (9 * (C1 + C2)) ** 0.5
+    bias = torch.randn(Cout, generator=gen)
+    xin = torch.cat([x1, x2], -1) if C2 else x1
+    ref = F.conv2d(xin[:, 0].permute(0, 3, 1, 2).double(), w.double(), bias.double(), padding=1).permute(0, 2, 3, 1)
+    wp, _, _ = packing.pack_conv3d(w.to(DEV).unsqueeze(2))
+    y, stats, ran_tc = run_conv(x1.to(DEV), wp, 9, x2=x2.to(DEV) if C2 else None, bias=bias.to(DEV), cout=Cout, pad=(0, 1, 1),
+                                kernel=(1, 3, 3), gn_groups=8, tcgen05=True)
+    assert ran_tc, "the 2-D 3x3 shape must be served by the tcgen05 kernel"
+    assert rel_err(y[:, 0], ref) <= TOL_TF32
+    v = y.double().reshape(N, -1, 8, Cout // 8)
+    assert torch.allclose(stats[:, :, 0], v.sum(dim=(1, 3)), rtol=1e-5, atol=1e-4)
+    assert torch.allclose(stats[:, :, 1], (v * v).sum(dim=(1, 3)), rtol=1e-5, atol=1e-4)
