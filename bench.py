@@ -1,16 +1,24 @@
 #!/usr/bin/env python
 """bench.py — denoising steps/sec on the 2-D smoke 64x64x32-frame configuration at batch 64 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--scaling strong|weak]
+                    [--config metric|smoke16+rollout|jellyfish128|smoke256x8|smoke128x64-ddim|burgers] [--precision tf32|3xtf32]
 
-A "step" is one iteration of GaussianDiffusion.p_sample_loop over a batch of 64 trajectories: joint U-Net forward,
-prior U-Net forward, guidance + prior re-weighting + posterior update + re-imposed initial condition, including the
-torch.randn noise draw.  Weak scaling: every rank owns its own batch of 64 trajectories (they never
-interact); `value` = batch-64 steps/s summed over ranks, timed on the device, max over ranks.
-Synthetic inputs and seeded default-init weights (no checkpoints/datasets are reachable).
+A "step" is one iteration of GaussianDiffusion.p_sample_loop over the batch: joint U-Net forward, prior U-Net forward,
+guidance + prior re-weighting + posterior update + re-imposed initial condition, including the torch.randn noise draw
+(SURVEY.md 8(d)).  Trajectories never interact, so ranks own disjoint slices of the batch:
 
---impl reference times the reference's algorithm on the host CPU cores: the oracle port (oracle/*.py — plain PyTorch
-fp32 restatement pinned to the unmodified reference by tests/golden) on a bounded sample of the same workload.
+  --scaling strong (default; BASELINE.json: "batch 64 at 1/2/4/8 B200"): the GLOBAL batch is 64, each rank
+      samples 64/N trajectories through diffphycon_b200.distributed.sample_sharded on a K-step schedule — global noise stream
+      sliced per rank (an N-rank run reproduces the 1-rank trajectories), the single NCCL all-gather of the sampled controls
+      INSIDE the timed region.  `value` = batch-64 steps/s.  At N > 1 the line also carries `weak` (64 per rank, no gather).
+  --scaling weak: every rank owns 64 trajectories; `value` = batch-64 steps/s summed over ranks.
+
+Timed on the device (CUDA events), max over ranks.  Synthetic inputs and seeded default-init weights (no checkpoints/datasets
+are reachable).  --config selects the other BASELINE.json configurations (their own metric names; see CONFIGS).
+
+--impl reference times the reference's algorithm on the host CPU cores: the oracle port (oracle/*.py — plain PyTorch fp32
+restatement pinned to the unmodified reference by tests/golden) on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -30,6 +38,16 @@ UNIT = "steps/s"
 FRAMES, SIZE, CH = 32, 64, 6
 FLOPS_PER_SAMPLE_STEP = 1.7945e12     # two U-Net forwards (908.8 + 885.7 GFLOP) per trajectory
 ALGO_BYTES_PER_SAMPLE_STEP = 7.93e9   # fused fp32 algorithmic minimum per trajectory
+
+CONFIGS = {
+    # name: (metric, BASELINE.json config it restates)
+    "metric": (METRIC, "metric row M"),
+    "smoke16+rollout": ("denoising steps/sec (2D smoke 64x64x32, batch 16) + phi rollout of the sampled controls", "configs[1]"),
+    "jellyfish128": ("denoising steps/sec (2D jellyfish 128x128x20, batch 8, joint + prior + surrogate-net guidance)", "configs[2]"),
+    "smoke256x8": ("denoising steps/sec (2D smoke 64x64x32, batch 256 over 8 GPUs = 32 per GPU)", "configs[3]"),
+    "smoke128x64-ddim": ("DDIM steps/sec (2D smoke 128x128x64, batch 64 over 8 GPUs = 8 per GPU, eta 1, guided)", "configs[4]"),
+    "burgers": ("denoising steps/sec (1D Burgers FOPC 16x128, two-model DDPM-200, batch 4)", "configs[0]"),
+}
 
 
 def peaks():
@@ -111,7 +129,7 @@ def run_reference(args, rank):
     sample = f"1 of 64 trajectories at the metric shape, {args.warmup} warm-up + {args.steps} timed steps, linear extrapolation to batch 64"
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 64.0 * sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 64.0 * sec * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "smoke 64x64x32 frames, batch 64, DDPM p_sample step (2 U-Nets + guidance + posterior)",
                    "note": "CPU reference arm does not use the GPUs; value is the host-core rate"},
@@ -139,6 +157,69 @@ def _emit(line):
     os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(line) + "\n").encode())
 
 
+def measure_tf32_peak(dev):
+    """cuBLAS TF32 GEMM 8192^3 (2*N^3 FLOP), best of 10 — the recipe MEASURED_PEAKS.json uses for bf16, in the arithmetic type the
+    convolutions compute in.  Library call, used only as the roofline denominator."""
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a, b = torch.randn(n, n, device=dev), torch.randn(n, n, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b)
+        torch.cuda.synchronize()
+        best = 1e9
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(10):
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2.0 * n ** 3 / (best / 1e3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def time_region(fn, barrier, dist, dev, world):
+    """CUDA-event time of fn() in ms, bracketed by barrier + synchronize, max over ranks."""
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    barrier()
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item()), out
+
+
+def smoke_nets(dpc, args, dev):
+    torch.manual_seed(0)
+    mj = dpc.Unet3D_with_Conv3D(dim=64, dim_mults=(1, 2, 4), channels=6)
+    mw = dpc.Unet3D_with_Conv3D(dim=64, dim_mults=(1, 2, 4), channels=2)
+    for m in (mj, mw):
+        m.precision = args.precision
+        m.use_tcgen05 = not args.no_tcgen05
+        m.micro_batch = args.micro_batch or None
+    return mj.to(dev), mw.to(dev)
+
+
+def smoke_diffusion(dpc, nets, dev, frames, size, timesteps=1000, sampling_timesteps=None, eta=0.0):
+    return dpc.GaussianDiffusion(list(nets), image_size=size, frames=frames, timesteps=timesteps,
+                                 sampling_timesteps=timesteps if sampling_timesteps is None else sampling_timesteps,
+                                 loss_type='l2', objective='pred_noise', standard_fixed_ratio=1e5, coeff_ratio=0,
+                                 eval_2ddpm=True, w_prob_exp=0.97, ddim_sampling_eta=eta).to(dev)
+
+
+def blob_init(B, size, dev):
+    yy, xx = torch.meshgrid(torch.linspace(-1, 1, size), torch.linspace(-1, 1, size), indexing="ij")
+    blob = torch.exp(-((xx - 0.1) ** 2 + (yy + 0.2) ** 2) / 0.1)
+    return (blob[None].repeat(B, 1, 1) / 2.0).to(dev).contiguous()
+
+
 def main():
     _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -146,13 +227,16 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="trajectories per GPU (the metric is quoted at 64)")
+    ap.add_argument("--config", default="metric", choices=list(CONFIGS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--batch", type=int, default=0, help="override the batch (metric: global batch for strong, per GPU for weak)")
     ap.add_argument("--precision", default="tf32", choices=["tf32", "3xtf32"])
     ap.add_argument("--micro-batch", type=int, default=0)
     ap.add_argument("--no-tcgen05", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-rollout", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -174,63 +258,94 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
-    torch.manual_seed(0)
-    mj = dpc.Unet3D_with_Conv3D(dim=64, dim_mults=(1, 2, 4), channels=6)
-    mw = dpc.Unet3D_with_Conv3D(dim=64, dim_mults=(1, 2, 4), channels=2)
-    for m in (mj, mw):
-        m.precision = args.precision
-        m.use_tcgen05 = not args.no_tcgen05
-        m.micro_batch = args.micro_batch or None
-    diff = dpc.GaussianDiffusion([mj, mw], image_size=SIZE, frames=FRAMES, timesteps=1000, sampling_timesteps=1000,
-                                 loss_type='l2', objective='pred_noise', standard_fixed_ratio=1e5, coeff_ratio=0,
-                                 eval_2ddpm=True, w_prob_exp=0.97).to(dev)
-    design_fn = dpc.StockSmokeGuidance(dpc.SMOKE_RESCALER, w_energy=0.0)
-    torch.manual_seed(1234 + rank)
-    yy, xx = torch.meshgrid(torch.linspace(-1, 1, SIZE), torch.linspace(-1, 1, SIZE), indexing="ij")
-    blob = torch.exp(-((xx - 0.1) ** 2 + (yy + 0.2) ** 2) / 0.1)
-    init = (blob[None].repeat(B, 1, 1) / 2.0).to(dev).contiguous()
-    shape = (B, FRAMES, CH, SIZE, SIZE)
-    x = torch.randn(shape, device=dev)
-    x[:, 0, 0] = init
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(xc, t):
-        xn, _ = diff.p_sample(shape, xc, t, None, design_fn=design_fn, design_guidance="standard", init=init,
-                              _impose_init=True)
+    if args.config != "metric":
+        run_other_config(args, dpc, _lib, dist, dev, rank, world, local_rank, barrier)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    from diffphycon_b200.distributed import sample_sharded, shard_bounds
+    K, W = args.steps, max(args.warmup, 0)
+    strong = args.scaling == "strong"
+    Bg = args.batch or 64                                   # strong: global batch; weak: per-rank batch
+    lo, hi = shard_bounds(Bg, world, rank) if strong else (0, Bg)
+    B = hi - lo                                             # trajectories this rank owns
+    nets = smoke_nets(dpc, args, dev)
+    diff = smoke_diffusion(dpc, nets, dev, FRAMES, SIZE)
+    design_fn = dpc.StockSmokeGuidance(dpc.SMOKE_RESCALER, w_energy=0.0)
+    torch.manual_seed(1234 + rank)
+    init_g = blob_init(Bg if strong else B, SIZE, dev)      # strong: the GLOBAL init, identical on every rank
+    init = init_g[lo:hi].contiguous() if strong else init_g
+    shape = (B, FRAMES, CH, SIZE, SIZE)
+    x = torch.randn(shape, device=dev)
+    x[:, 0, 0] = init
+
+    def step(xc, t, ini=init, shp=shape):
+        xn, _ = diff.p_sample(shp, xc, t, None, design_fn=design_fn, design_guidance="standard", init=ini, _impose_init=True)
         return xn
 
     t_cur = 999
-    for _ in range(args.warmup):
+    for _ in range(W):
         x = step(x, t_cur)
         t_cur -= 1
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     launches0 = _lib.LaunchCounter.count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        x = step(x, t_cur)
-        t_cur -= 1
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    gather = None
+    if strong:
+        # the public multi-GPU call: a K-step schedule through sample_sharded, global noise stream, one all-gather of the controls
+        diff_k = smoke_diffusion(dpc, nets, dev, FRAMES, SIZE, timesteps=K)
+        if world > 1:                                       # NCCL communicator / gather buffers are set up outside the timed region
+            warm = torch.zeros(shard_bounds(Bg, world, 0)[1], FRAMES, 2, SIZE, SIZE, device=dev)
+            bucket = torch.empty(world * warm.shape[0], *warm.shape[1:], device=dev)
+            dist.all_gather_into_tensor(bucket, warm)
+            del warm, bucket
+        torch.manual_seed(4321)                             # same generator state on every rank: global noise, sliced per rank
+        ms, ctrl = time_region(lambda: sample_sharded(diff_k, Bg, design_fn=design_fn, design_guidance="standard", init=init_g,
+                                                      global_noise=True, gather_channels=slice(3, 5)),
+                               barrier, dist, dev, world)
+        assert ctrl.shape[0] == Bg and torch.isfinite(ctrl).all(), "non-finite sampled controls"
+        gather = {"collective": "all_gather_into_tensor(sampled controls), inside the timed region" if world > 1 else "none (1 rank)",
+                  "bytes_per_rank": int(ctrl.numel() // max(world, 1)) * 4, "once_per_sampling_run": True}
+        ms_per_step = ms / K
+        value = (Bg / 64.0) / (ms_per_step / 1e3)
+    else:
+        def loop():
+            nonlocal x, t_cur
+            for _ in range(K):
+                x = step(x, t_cur)
+                t_cur -= 1
+        ms, _ = time_region(loop, barrier, dist, dev, world)
+        assert torch.isfinite(x).all(), "non-finite state after the timed steps"
+        ms_per_step = ms / K
+        value = world * (B / 64.0) / (ms_per_step / 1e3)
     launches = _lib.LaunchCounter.count - launches0
     sampler.stop_flag = True
-    barrier()
-    ms_t = torch.tensor([ms], device=dev)
-    if world > 1:
-        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms_max = float(ms_t.item())
-    assert torch.isfinite(x).all(), "non-finite state after the timed steps"
-    ms_per_step = ms_max / args.steps
-    value = world * (B / 64.0) / (ms_per_step / 1e3)
+
+    # ---- secondary: weak scaling (64 trajectories per rank, no collective) when the headline is strong and N > 1 ----
+    weak = None
+    if strong and world > 1:
+        Bw = 64
+        xw = torch.randn(Bw, FRAMES, CH, SIZE, SIZE, device=dev)
+        iw = blob_init(Bw, SIZE, dev)
+        xw[:, 0, 0] = iw
+        shw = tuple(xw.shape)
+        xw = step(xw, 500, iw, shw)
+
+        def loop_w():
+            nonlocal xw
+            for i in range(K):
+                xw = step(xw, 499 - i, iw, shw)
+        ms_w, _ = time_region(loop_w, barrier, dist, dev, world)
+        weak = {"per_gpu_batch": Bw, "ms_per_step": ms_w / K, "value": world * (Bw / 64.0) / (ms_w / K / 1e3), "unit": UNIT}
+        del xw
 
     # ---- end-to-end through the public API with HOST buffers (pinned), copies inside the timed region ----
     e2e = None
@@ -240,135 +355,277 @@ def main():
         hout = torch.empty(shape, dtype=torch.float32, pin_memory=True)
         hinit = torch.empty(init.shape, dtype=torch.float32, pin_memory=True)
         hinit.copy_(init)
-        n_e2e = max(2, min(args.steps, 3))
-        barrier()
-        e0.record()
-        for i in range(n_e2e):
-            xd = hx.to(dev, non_blocking=True)
-            idv = hinit.to(dev, non_blocking=True)
-            xn, _ = diff.p_sample(shape, xd, t_cur - i, None, design_fn=design_fn, design_guidance="standard", init=idv,
-                                  _impose_init=True)
-            hout.copy_(xn, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-            hx, hout = hout, hx
-        e1.record()
-        torch.cuda.synchronize()
-        ms_e = torch.tensor([e0.elapsed_time(e1) / n_e2e], device=dev)
-        if world > 1:
-            dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+        n_e2e = max(10, min(K, 20))
+        state = {"hx": hx, "hout": hout}
+
+        def loop_e2e():
+            for i in range(n_e2e):
+                xd = state["hx"].to(dev, non_blocking=True)
+                idv = hinit.to(dev, non_blocking=True)
+                xn, _ = diff.p_sample(shape, xd, 900 - i, None, design_fn=design_fn, design_guidance="standard", init=idv,
+                                      _impose_init=True)
+                state["hout"].copy_(xn, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                state["hx"], state["hout"] = state["hout"], state["hx"]
+        ms_e, _ = time_region(loop_e2e, barrier, dist, dev, world)
         nbytes = x.numel() * 4
-        e2e = {"value": world * (B / 64.0) / (float(ms_e.item()) / 1e3), "unit": UNIT,
-               "h2d_bytes_per_step": nbytes + init.numel() * 4, "d2h_bytes_per_step": nbytes, "steps": n_e2e}
+        units = (Bg / 64.0) if strong else world * (B / 64.0)
+        e2e = {"value": units / (ms_e / n_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": nbytes + init.numel() * 4,
+               "d2h_bytes_per_step": nbytes, "steps": n_e2e,
+               "note": "per-rank pinned host state copied in and out around every p_sample call"}
 
-    # ---- dominant kernel (3x3x3 conv 64->64 at 32x64x64, the most frequent layer) timed alone on its stream ----
     roof = None
-    if rank == 0:
-        from diffphycon_b200 import packing
-        pk = peaks()
-        Bc = min(B, 16)
-        xa = torch.randn(Bc, FRAMES, SIZE, SIZE, 64, device=dev)
-        w = torch.randn(64, 64, 3, 3, 3, device=dev) / (27 * 64) ** 0.5
-        wp, _, _ = packing.pack_conv3d(w)
-        bias = torch.zeros(64, device=dev)
-        taps = packing.tap_table(3, 3, 3, SIZE, SIZE, dev)
-        y = torch.empty_like(xa)
-        stats = torch.zeros(Bc, 8, 2, dtype=torch.float64, device=dev)
-        p = _lib.ConvParams()
-        p.x1, p.C1, p.C2 = xa.data_ptr(), 64, 0
-        p.w, p.bias, p.y, p.taps, p.ntaps = wp.data_ptr(), bias.data_ptr(), y.data_ptr(), taps.data_ptr(), 27
-        p.gn_stats, p.gn_groups = stats.data_ptr(), 8
-        p.B, p.Fi, p.Hi, p.Wi, p.Fo, p.Ho, p.Wo = Bc, FRAMES, SIZE, SIZE, FRAMES, SIZE, SIZE
-        p.st = p.sh = p.sw = 1
-        p.pt = p.ph = p.pw = 1
-        p.oh_mul = p.ow_mul = 1
-        p.Hfull, p.Wfull = SIZE, SIZE
-        p.Cout, p.Npad, p.Kpad = 64, wp.shape[0], wp.shape[1]
-        used_tc = False
-        for _ in range(3):
-            used_tc = _lib.conv(p, tcgen05=not args.no_tcgen05)
-        torch.cuda.synchronize()
-        reps = 10
-        e0.record()
-        for _ in range(reps):
-            _lib.conv(p, tcgen05=not args.no_tcgen05)
-        e1.record()
-        torch.cuda.synchronize()
-        kms = e0.elapsed_time(e1) / reps
-        flops = 2.0 * Bc * FRAMES * SIZE * SIZE * 64 * 64 * 27
-        ach = flops / (kms / 1e3) / 1e12
-        traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
-        try:
-            tj = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_dominant_kernel_traffic.json")))
-            if used_tc and tj.get("kernel_batch") == Bc:
-                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-        except (OSError, ValueError, KeyError):
-            traffic = None
-        roof = {"bound": "tensor", "achieved": ach, "peak": pk["tensor_burst"], "unit": "TFLOP/s",
-                "frac": ach / pk["tensor_burst"], "frac_of_tf32_roof": ach / (pk["tensor_burst"] / 2), "traffic": traffic,
-                "traffic_note": "bytes per launch (ncu, profiles/r1_ncu_full_v12.txt); algorithmic = %d" % (2 * Bc * FRAMES * SIZE * SIZE * 64 * 4),
-                "kernel": "conv3d_tcgen05 3x3x3 64->64" if used_tc else "conv_igemm (mma.sync) 3x3x3 64->64",
-                "kernel_ms": kms, "kernel_batch": Bc, "peak_source": pk["source"] + " bf16 burst (kernel timed alone); TF32 nominal peak is half of bf16",
-                "step_tensor_tflops": FLOPS_PER_SAMPLE_STEP * B / (ms_per_step / 1e3) / 1e12,
-                "step_tensor_frac_of_sustained_bf16": FLOPS_PER_SAMPLE_STEP * B / (ms_per_step / 1e3) / 1e12 / pk["tensor_sustained"],
-                "step_hbm_algorithmic_gbs": ALGO_BYTES_PER_SAMPLE_STEP * B / (ms_per_step / 1e3) / 1e9,
-                "step_hbm_frac": ALGO_BYTES_PER_SAMPLE_STEP * B / (ms_per_step / 1e3) / 1e9 / pk["hbm"]}
-
-    # ---- the single collective of the path: all-gather of the sampled controls [B,32,2,64,64] per rank (untimed step) ----
-    gather = None
-    if world > 1:
-        ctrl_local = x[:, :, 3:5].contiguous()
-        bucket = torch.empty(world * ctrl_local.shape[0], *ctrl_local.shape[1:], dtype=ctrl_local.dtype, device=dev)
-        dist.all_gather_into_tensor(bucket, ctrl_local)       # warm-up (NCCL communicator setup)
-        barrier()
-        e0.record()
-        dist.all_gather_into_tensor(bucket, ctrl_local)
-        e1.record()
-        torch.cuda.synchronize()
-        g_ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        dist.all_reduce(g_ms, op=dist.ReduceOp.MAX)
-        gather = {"collective": "all_gather(sampled controls)", "bytes_per_rank": ctrl_local.numel() * 4,
-                  "ms": float(g_ms.item()), "once_per_sampling_run": True}
+    if rank == 0 and not args.no_roofline:
+        roof = dominant_kernel_roofline(args, _lib, dev, ms_per_step, Bg if strong else B * world)
 
     # ---- post-sampling rollout of the sampled controls, informational ----
     rollout = None
     if rank == 0 and not args.no_rollout:
-        from diffphycon_b200 import smoke_rollout as sr
-        sim = sr.init_sim_128()
-        ctrl = (x[:, :, 3:5] * torch.tensor([16.0, 20.0], device=dev).view(1, 1, 2, 1, 1)).contiguous()
-        c1, c2 = ctrl[:, :, 0].contiguous(), ctrl[:, :, 1].contiguous()
-        dens = (x[:, 0, 0] * 2.0).clamp(min=0).contiguous()
-        sr.solver_batch(sim, sr.init_velocity_(), dens[:1], c1[:1, :4].contiguous(), c2[:1, :4].contiguous(), 8)
-        torch.cuda.synchronize()
-        e0.record()
-        ro = sr.solver_batch(sim, sr.init_velocity_(), dens, c1, c2, 256)
-        e1.record()
-        torch.cuda.synchronize()
-        rms = e0.elapsed_time(e1)
-        rollout = {"trajectories": B, "frames": 256, "ms_total": rms, "trajectories_per_s": B / (rms / 1e3),
-                   "mean_cg_iterations": float(ro["iterations"][:, 1:].float().mean()),
-                   "note": "one persistent CTA per trajectory, fp64 CG with the reference's 500-iteration cap; the "
-                           "reference needs ~48 s per trajectory on one CPU core (SURVEY.md section 6)"}
+        rollout = run_rollout(dpc, x, dev)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, sec, cores = cpu_reference_steps_per_s(2, 1)
+        v2, sec2, _ = cpu_reference_steps_per_s(1, 1, batch_cpu=2)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "1 of 64 trajectories at the metric shape, 1 warm-up + 2 timed steps (%.1f s/step), linear extrapolation to batch 64" % sec}
+               "sample": "1 of 64 trajectories at the metric shape, 1 warm-up + 2 timed steps (%.1f s/step), linear extrapolation to "
+                         "batch 64; linearity check at 2 trajectories: %.1f s/step = %.2fx the 1-trajectory step" % (sec, sec2, sec2 / sec),
+               "value_from_batch2": v2}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "tf32" if args.precision == "tf32" else "f32(3xtf32)", "data": "synthetic",
             "config": {"workload": "smoke 64x64x32 frames, DDPM p_sample step (joint+prior Unet3D dim64 (1,2,4), stock guidance, posterior)",
-                       "per_gpu_batch": B, "global_batch": B * world, "sharding": "independent trajectories per rank, no per-step collective",
+                       "per_gpu_batch": B, "global_batch": Bg if strong else B * world,
+                       "sharding": ("global batch 64 sliced over ranks (sample_sharded), one all-gather of the controls per sampling run"
+                                    if strong else "independent trajectories per rank, no collective"),
                        "l2": "inputs larger than L2 (activations are GBs per layer)", "precision": args.precision,
                        "tcgen05": not args.no_tcgen05, "micro_batch": args.micro_batch or None},
-            "clocks": sampler.summary(), "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu, "rollout": rollout, "gather": gather,
+            "clocks": sampler.summary(), "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
+            "rollout": rollout, "gather": gather, "weak": weak,
         }
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def dominant_kernel_roofline(args, _lib, dev, ms_per_step, B_global):
+    """The dominant kernel (3x3x3 conv 64->64 at 32x64x64, the most frequent layer) timed alone on its stream."""
+    from diffphycon_b200 import packing
+    pk = peaks()
+    Bc = 16
+    xa = torch.randn(Bc, FRAMES, SIZE, SIZE, 64, device=dev)
+    w = torch.randn(64, 64, 3, 3, 3, device=dev) / (27 * 64) ** 0.5
+    wp, _, _ = packing.pack_conv3d(w)
+    bias = torch.zeros(64, device=dev)
+    taps = packing.tap_table(3, 3, 3, SIZE, SIZE, dev)
+    y = torch.empty_like(xa)
+    stats = torch.zeros(Bc, 8, 2, dtype=torch.float64, device=dev)
+    p = _lib.ConvParams()
+    p.x1, p.C1, p.C2 = xa.data_ptr(), 64, 0
+    p.w, p.bias, p.y, p.taps, p.ntaps = wp.data_ptr(), bias.data_ptr(), y.data_ptr(), taps.data_ptr(), 27
+    p.gn_stats, p.gn_groups = stats.data_ptr(), 8
+    p.B, p.Fi, p.Hi, p.Wi, p.Fo, p.Ho, p.Wo = Bc, FRAMES, SIZE, SIZE, FRAMES, SIZE, SIZE
+    p.st = p.sh = p.sw = 1
+    p.pt = p.ph = p.pw = 1
+    p.oh_mul = p.ow_mul = 1
+    p.Hfull, p.Wfull = SIZE, SIZE
+    p.Cout, p.Npad, p.Kpad = 64, wp.shape[0], wp.shape[1]
+    used_tc = False
+    for _ in range(3):
+        used_tc = _lib.conv(p, tcgen05=not args.no_tcgen05)
+    torch.cuda.synchronize()
+    reps = 10
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        _lib.conv(p, tcgen05=not args.no_tcgen05)
+    e1.record()
+    torch.cuda.synchronize()
+    kms = e0.elapsed_time(e1) / reps
+    flops = 2.0 * Bc * FRAMES * SIZE * SIZE * 64 * 64 * 27
+    ach = flops / (kms / 1e3) / 1e12
+    del xa, y
+    tf32_peak = measure_tf32_peak(dev)
+    traffic, traffic_src = None, None   # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the committed ncu --set full capture
+    for name in ("r2_dominant_kernel_traffic.json", "r1_dominant_kernel_traffic.json"):
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", name)))
+            if used_tc and tj.get("kernel_batch") == Bc:
+                traffic, traffic_src = tj["dram_bytes_read"] + tj["dram_bytes_write"], name
+                break
+        except (OSError, ValueError, KeyError):
+            continue
+    step_tflops = FLOPS_PER_SAMPLE_STEP * B_global / (ms_per_step / 1e3) / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": pk["tensor_burst"], "unit": "TFLOP/s",
+            "frac": ach / pk["tensor_burst"], "tf32_peak_measured": tf32_peak, "frac_of_tf32_peak_measured": ach / tf32_peak,
+            "traffic": traffic,
+            "traffic_note": "bytes per launch (ncu --set full, profiles/%s); algorithmic = %d" % (traffic_src, 2 * Bc * FRAMES * SIZE * SIZE * 64 * 4),
+            "kernel": "conv3d_tcgen05 3x3x3 64->64" if used_tc else "conv_igemm (mma.sync) 3x3x3 64->64",
+            "kernel_ms": kms, "kernel_batch": Bc,
+            "peak_source": pk["source"] + " bf16 burst (kernel timed alone); tf32_peak_measured = cuBLAS TF32 GEMM 8192^3, best of 10, this run",
+            "step_tensor_tflops": step_tflops,
+            "step_tensor_frac_of_sustained_bf16": step_tflops / pk["tensor_sustained"],
+            "step_tensor_frac_of_tf32_peak_measured": step_tflops / tf32_peak,
+            "step_hbm_algorithmic_gbs": ALGO_BYTES_PER_SAMPLE_STEP * B_global / (ms_per_step / 1e3) / 1e9,
+            "step_hbm_frac": ALGO_BYTES_PER_SAMPLE_STEP * B_global / (ms_per_step / 1e3) / 1e9 / pk["hbm"]}
+
+
+def run_rollout(dpc, x, dev, frames=256):
+    from diffphycon_b200 import smoke_rollout as sr
+    B = x.shape[0]
+    sim = sr.init_sim_128()
+    ctrl = (x[:, :, 3:5] * torch.tensor([16.0, 20.0], device=dev).view(1, 1, 2, 1, 1)).contiguous()
+    c1, c2 = ctrl[:, :, 0].contiguous(), ctrl[:, :, 1].contiguous()
+    dens = (x[:, 0, 0] * 2.0).clamp(min=0).contiguous()
+    sr.solver_batch(sim, sr.init_velocity_(), dens[:1], c1[:1, :4].contiguous(), c2[:1, :4].contiguous(), 8)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    ro = sr.solver_batch(sim, sr.init_velocity_(), dens, c1, c2, frames)
+    e1.record()
+    torch.cuda.synchronize()
+    rms = e0.elapsed_time(e1)
+    return {"trajectories": B, "frames": frames, "ms_total": rms, "trajectories_per_s": B / (rms / 1e3),
+            "mean_cg_iterations": float(ro["iterations"][:, 1:].float().mean()),
+            "note": "one persistent CTA per trajectory, fp64 CG with the reference's 500-iteration cap; the "
+                    "reference needs ~48 s per trajectory on one CPU core (SURVEY.md section 6)"}
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# the other BASELINE.json configurations
+# ------------------------------------------------------------------------------------------------------------------------
+def run_other_config(args, dpc, _lib, dist, dev, rank, world, local_rank, barrier):
+    K, W = args.steps, max(args.warmup, 0)
+    metric, which = CONFIGS[args.config]
+    sampler = ClockSampler(local_rank)
+    extra = {}
+    design_fn = dpc.StockSmokeGuidance(dpc.SMOKE_RESCALER, w_energy=0.0)
+    torch.manual_seed(1234 + rank)
+    if args.config in ("smoke16+rollout", "smoke256x8", "smoke128x64-ddim"):
+        frames, size = (64, 128) if args.config == "smoke128x64-ddim" else (FRAMES, SIZE)
+        B = args.batch or {"smoke16+rollout": 16, "smoke256x8": 32, "smoke128x64-ddim": 8}[args.config]
+        nets = smoke_nets(dpc, args, dev)
+        ddim = args.config == "smoke128x64-ddim"
+        diff = smoke_diffusion(dpc, nets, dev, frames, size, sampling_timesteps=250 if ddim else None, eta=1.0 if ddim else 0.0)
+        init = blob_init(B, size, dev)
+        shape = (B, frames, CH, size, size)
+        x = torch.randn(shape, device=dev)
+        x[:, 0, 0] = init
+        if ddim:
+            times = list(reversed(torch.linspace(-1, 999, steps=251).int().tolist()))
+            pairs = list(zip(times[:-1], times[1:]))
+
+            def step(xc, i):
+                return diff.ddim_step(xc, pairs[i][0], pairs[i][1], design_fn=design_fn, design_guidance="standard", init=init)
+        else:
+            def step(xc, i):
+                return diff.p_sample(shape, xc, 999 - i, None, design_fn=design_fn, design_guidance="standard", init=init,
+                                     _impose_init=True)[0]
+        units_per_step = world * B      # trajectories advanced per step over all ranks
+        flops_step = (FLOPS_PER_SAMPLE_STEP if size == 64 else (7359.4e9 + 7174.7e9)) * B   # SURVEY.md 8(d)
+        workload = f"smoke {size}x{size}x{frames} frames, {'DDIM-250 eta 1' if ddim else 'DDPM'} step, {B} trajectories per GPU"
+    elif args.config == "jellyfish128":
+        from diffphycon_b200 import diffusion_2d_jellyfish as dj
+        B, frames, size = args.batch or 8, 20, 128
+        torch.manual_seed(0)
+        mj = dpc.Unet3D_with_Conv3D(dim=64, dim_mults=(1, 2, 4), channels=7, out_dim=4)
+        mw = dpc.Unet3D_with_Conv3D(dim=64, dim_mults=(1, 2, 4), channels=7, out_dim=1)
+        fm = dpc.ForceUnet(dim=64, out_dim=1, dim_mults=(1, 2, 4, 8), channels=4)
+        bd = dpc.Unet(dim=64, out_dim=3, dim_mults=(1, 2, 4, 8), channels=3)
+        for m in (mj, mw, fm, bd):
+            m.precision = args.precision
+            m.use_tcgen05 = not args.no_tcgen05
+            m.to(dev)
+        diff = dj.GaussianDiffusion([mj, mw], image_size=size, frames=frames, cond_steps=1, timesteps=1000, sampling_timesteps=1000,
+                                    loss_type='l2', objective='pred_noise', coeff_ratio_J=0.3, coeff_ratio_w=0.3, eval_2ddpm=True,
+                                    w_prob_exp=0.7, use_guidance_in_model_predictions=False).to(dev)
+        guidance = dpc.JellyfishGuidance(fm, bd, p_min=-1.5, p_max=2.5, reg_ratio=1000.0)
+        torch.manual_seed(1234 + rank)
+        state_0 = torch.rand(B, 3, size, size, device=dev) * 2 - 1
+        bd_0 = torch.cat([(torch.rand(B, 1, size, size, device=dev) > 0.7).float(), torch.rand(B, 2, size, size, device=dev) - 0.5], 1)
+        thetas_0 = torch.rand(B, device=dev) * 0.7 + 0.2
+        st = diff._begin((B, frames, 7, size, size), [state_0, bd_0], thetas_0, bd)
+
+        def step(_x, i):
+            diff._ddpm_step(st, 999 - i, guidance, "standard-alpha")
+            return st.x
+        x = st.x
+        units_per_step = world * B
+        # SURVEY.md 8(a) A11: per sample-step at 64^2 2 x 570 + 292 + ~3 x (292 + 83) GF, x 4 at 128^2
+        flops_step = 4 * (2 * 570e9 + 292e9 + 3 * (292e9 + 83e9)) * B
+        workload = (f"jellyfish {size}x{size}x{frames}, DDPM step: joint + prior Unet3D (7->4, 7->1), force_fn guidance = ForceUnet + "
+                    f"boundary-updater Unet forward AND backward on the engine, update_bd forward; {B} trajectories per GPU")
+    elif args.config == "burgers":
+        from diffphycon_b200 import diffusion_1d_burgers as db
+        from diffphycon_b200.burgers_unet import Unet2D
+        from diffphycon_b200.burgers import burgers_numeric_solve_free
+        B, T = args.batch or 4, 200
+        torch.manual_seed(0)
+        uw = Unet2D(dim=64, out_dim=2, dim_mults=(1, 2, 4), channels=2, resnet_block_groups=1).to(dev)
+        w_ = Unet2D(dim=32, out_dim=2, dim_mults=(1, 2, 4, 8), channels=2, resnet_block_groups=1).to(dev)
+        uw.precision = w_.precision = args.precision
+        diff = db.GaussianDiffusion((uw, w_), seq_length=(16, 128), timesteps=T, auto_normalize=False, use_conv2d=True, temporal=True,
+                                    is_condition_u0=True, is_condition_uT=True, eval_two_models=True, prior_beta=1.5).to(dev)
+        xs = torch.linspace(0, 1, 130, device=dev)[1:-1]
+        u0 = torch.exp(-((xs[None] - torch.rand(B, 1, device=dev)) ** 2) * 50) - 0.5 * torch.exp(-((xs[None] - torch.rand(B, 1, device=dev)) ** 2) * 80)
+        f0 = torch.zeros(B, 10, 128, device=dev)
+        target = burgers_numeric_solve_free(u0, f0, visc=0.01, T=1.0, dt=1e-4, num_t=10)
+        kw = dict(nablaJ=db.get_nablaJ(lambda xx: torch.zeros(xx.shape[0], device=xx.device) + 0.0 * xx.sum((1, 2, 3))),
+                  J_scheduler=db.cosine_beta_J_schedule, w_scheduler=db.sigmoid_schedule_flip, u_init=target[:, 0] / 10,
+                  u_final=target[:, 10] / 10)
+        x = None
+
+        def run_all(_x, i):        # one "step" call = one full 200-step sampling run + the finite-difference rollout of its controls
+            y = diff.sample(batch_size=B, clip_denoised=True, guidance_u0=True, **kw)
+            extra["rollout_traj"] = burgers_numeric_solve_free(u0, (y[:, 1, :10] * 10).contiguous(), visc=0.01, T=1.0, dt=1e-4, num_t=10)
+            return y
+        step = run_all
+        units_per_step = None
+        flops_step = 32.1e9 * T
+        workload = f"Burgers FOPC two-model DDPM, {T} steps, [{B},2,16,128], + 10 000-step finite-difference rollout per run"
+    else:
+        raise AssertionError(args.config)
+
+    for i in range(W):
+        x = step(x, i)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.LaunchCounter.count
+
+    def loop():
+        nonlocal x
+        for i in range(K):
+            x = step(x, W + i)
+    ms, _ = time_region(loop, barrier, dist, dev, world)
+    launches = _lib.LaunchCounter.count - launches0
+    sampler.stop_flag = True
+    assert torch.isfinite(x).all()
+    if args.config == "burgers":
+        ms_per_step = ms / (K * 200)
+        value = 1e3 / ms_per_step
+    else:
+        ms_per_step = ms / K
+        value = 1e3 / ms_per_step          # steps/s of the config's whole (global) batch
+    rollout = None
+    if args.config == "smoke16+rollout" and rank == 0 and not args.no_rollout:
+        rollout = run_rollout(dpc, x, dev)
+    pk = peaks()
+    if rank == 0:
+        line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "tf32" if args.precision == "tf32" else "f32(3xtf32)", "data": "synthetic",
+                "config": {"workload": workload, "baseline_config": which, "global_batch": units_per_step, "precision": args.precision,
+                           "tcgen05": not args.no_tcgen05},
+                "clocks": sampler.summary(), "gpu_launches": launches,
+                "roofline": {"bound": "tensor", "achieved": flops_step / (ms_per_step / 1e3) / 1e12, "peak": pk["tensor_sustained"],
+                             "unit": "TFLOP/s", "frac": flops_step / (ms_per_step / 1e3) / 1e12 / pk["tensor_sustained"], "traffic": None,
+                             "kernel": "whole step of ONE GPU (SURVEY.md 8(d) FLOP counts per trajectory x per-GPU batch)",
+                             "peak_source": pk["source"] + " bf16 sustained"},
+                "rollout": rollout, "e2e": None, "cpu_baseline": None}
+        _emit(line)
 
 
 if __name__ == "__main__":

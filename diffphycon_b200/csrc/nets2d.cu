@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(LB_PIX)
 linattn_bwd_apply_kernel(const float* __restrict__ qkv, const float* __restrict__ ctx, const float* __restrict__ kstat,
                          const float* __restrict__ dctx, const float* __restrict__ dout, float* __restrict__ dqkv, int HW,
                          int heads, float scale, float vscale) {
-  extern __shared__ float smf[];
+  extern __shared__ __align__(16) float smf[];
   float* s_ctx = smf;                       // [d][e]
   float* s_dctx = smf + DH * DH;            // [d][e]
   float* s_sk = smf + 2 * DH * DH;          // [d]
@@ -382,11 +382,15 @@ linattn_bwd_apply_kernel(const float* __restrict__ qkv, const float* __restrict_
     float a = 0.f, b = 0.f;
     const float ksd = kr[d];
 #pragma unroll
-    for (int e = 0; e < DH; ++e) {
-      const float c = s_ctx[d * DH + e], dc = s_dctx[d * DH + e];
-      a = fmaf(c, dov[e], a);            // dqs[d]
-      b = fmaf(dc, vv[e], b);            // dks[d]
-      dv[e] = fmaf(ksd, dc, dv[e]);
+    for (int e = 0; e < DH; e += 4) {      // broadcast LDS.128: 2 shared loads per 12 FMAs
+      const float4 c = *reinterpret_cast<const float4*>(&s_ctx[d * DH + e]);
+      const float4 dc = *reinterpret_cast<const float4*>(&s_dctx[d * DH + e]);
+      a = fmaf(c.x, dov[e], fmaf(c.y, dov[e + 1], fmaf(c.z, dov[e + 2], fmaf(c.w, dov[e + 3], a))));       // dqs[d]
+      b = fmaf(dc.x, vv[e], fmaf(dc.y, vv[e + 1], fmaf(dc.z, vv[e + 2], fmaf(dc.w, vv[e + 3], b))));       // dks[d]
+      dv[e] = fmaf(ksd, dc.x, dv[e]);
+      dv[e + 1] = fmaf(ksd, dc.y, dv[e + 1]);
+      dv[e + 2] = fmaf(ksd, dc.z, dv[e + 2]);
+      dv[e + 3] = fmaf(ksd, dc.w, dv[e + 3]);
     }
     dqs[d] = a;
     dot = fmaf(a, sr[d], dot);
