@@ -237,6 +237,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-rollout", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="after the timed region, print a per-launch-category CUDA-event breakdown "
+                                                           "of one more step to stderr (development aid)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -603,6 +605,14 @@ def run_other_config(args, dpc, _lib, dist, dev, rank, world, local_rank, barrie
     launches = _lib.LaunchCounter.count - launches0
     sampler.stop_flag = True
     assert torch.isfinite(x).all()
+    if args.profile and rank == 0:
+        with _lib.Profiler() as prof:
+            x = step(x, W + K)
+        summ = prof.summary()
+        tot = sum(t for _, t in summ.values())
+        for k, (n, t) in sorted(summ.items(), key=lambda kv: -kv[1][1])[:45]:
+            sys.stderr.write(f"{t:9.2f} ms {100 * t / tot:5.1f}% n={n:4d} {k}\n")
+        sys.stderr.write(f"profiled step total {tot:.2f} ms\n")
     if args.config == "burgers":
         ms_per_step = ms / (K * 200)
         value = 1e3 / ms_per_step

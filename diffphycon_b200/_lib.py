@@ -80,6 +80,8 @@ _SIGNATURES = {
                              C.c_int),
     "dpc_ddim_guided_step": ([c_fp] * 6 + [C.c_int32, C.POINTER(StepCoefs), c_fp, c_fp] + [C.c_int32] * 4 + [c_fp],
                              C.c_int),
+    "dpc_sampler_prepare": ([c_fp] * 3 + [C.c_int32, c_fp, C.c_int32, c_fp, c_fp], C.c_int),
+    "dpc_guided_step_dev": ([C.c_int32] + [c_fp] * 10 + [C.c_int32] * 4 + [c_fp], C.c_int),
     "dpc_predict_x_start": ([c_fp, c_fp, C.c_float, C.c_float, C.c_int32, c_fp, C.c_int64, c_fp], C.c_int),
     "dpc_burgers_model_output": ([c_fp] * 5 + [C.c_int32] + [C.c_float] * 4 + [C.c_int32, C.c_int64, C.c_int64, c_fp], C.c_int),
     "dpc_ddpm_posterior_step": ([c_fp] * 7 + [C.c_float] * 3 + [C.c_int32] + [C.c_float] * 3 + [C.c_int64, c_fp], C.c_int),
@@ -175,6 +177,7 @@ def device_guarded(fn):
 class LaunchCounter:
     """Counts kernel launches issued through this binding (bench.py reports it as gpu_launches)."""
     count = 0
+    graph_launches = 0     # CUDA-graph replays (each replays every kernel of one captured denoising step)
 
 
 class Profiler:
@@ -367,6 +370,20 @@ def guided_step(ddim, x, eps_joint, eps_w, noise, init, g, coefs: StepCoefs, x_o
     fn = lib().dpc_ddim_guided_step if ddim else lib().dpc_ddpm_guided_step
     check(fn(ptr(x), ptr(eps_joint), ptr(eps_w), ptr(noise), ptr(init), ptr(g), 1 if g is None else 0, C.byref(coefs),
              ptr(x_out), ptr(x_start_out), B, F, H, W, stream_ptr()), "dpc_guided_step")
+    LaunchCounter.count += 1
+
+
+@_timed("sampler_prepare")
+def sampler_prepare(t_table, c_table, step_index, nsteps, tt, B, cur):
+    check(lib().dpc_sampler_prepare(ptr(t_table), ptr(c_table), ptr(step_index), nsteps, ptr(tt), B, ptr(cur), stream_ptr()),
+          "dpc_sampler_prepare")
+    LaunchCounter.count += 1
+
+
+@_timed("guided_step")
+def guided_step_dev(ddim, x, eps_joint, eps_w, noise, init, coefs_host: StepCoefs, coefs_dev, x_out, x_start_out, B, F, H, W):
+    check(lib().dpc_guided_step_dev(1 if ddim else 0, ptr(x), ptr(eps_joint), ptr(eps_w), ptr(noise), ptr(init), C.byref(coefs_host),
+                                    ptr(coefs_dev), ptr(x_out), ptr(x_start_out), B, F, H, W, stream_ptr()), "dpc_guided_step_dev")
     LaunchCounter.count += 1
 
 

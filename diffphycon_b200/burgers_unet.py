@@ -153,6 +153,19 @@ class Unet2D(nn.Module):
         out += [("final_res_block", self.final_res_block)]
         return out
 
+    def invalidate_packed(self):
+        """Drop the packed weight copies; call after editing weights through `.data` (see Unet3D_with_Conv3D.invalidate_packed)."""
+        self._packed = None
+        self._packed_key = None
+
+    def load_state_dict(self, *a, **k):
+        self.invalidate_packed()
+        return super().load_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate_packed()
+        return super()._apply(fn, *a, **k)
+
     def _ensure_packed(self, dev):
         key = (str(dev), self.precision, tuple((p.data_ptr(), p._version) for p in self.parameters()))
         if self._packed is not None and self._packed_key == key:
@@ -401,9 +414,6 @@ class Unet2D(nn.Module):
 
 
 def Unet3D_pool(device) -> _Pool:
-    """The per-device buffer pool shared with Unet3D_with_Conv3D."""
-    from .unet3d import Unet3D_with_Conv3D
-    p = Unet3D_with_Conv3D._pools.get(device)
-    if p is None:
-        p = Unet3D_with_Conv3D._pools[device] = _Pool(device)
-    return p
+    """The per-(device, stream) buffer pool shared with Unet3D_with_Conv3D."""
+    from .unet3d import pool_for
+    return pool_for(device)

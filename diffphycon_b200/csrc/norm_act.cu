@@ -11,9 +11,9 @@ namespace dpc {
 // double (sum, sumsq) statistics the conv epilogue accumulated.
 template <bool VEC4>
 __global__ void __launch_bounds__(256)
-groupnorm_silu_kernel(const float* __restrict__ y, const double* __restrict__ stats, const float* __restrict__ gamma,
+groupnorm_silu_kernel(const float* y, const double* __restrict__ stats, const float* __restrict__ gamma,
                       const float* __restrict__ beta, const float* __restrict__ scale_shift, int64_t ss_stride,
-                      int64_t ss_off, const float* __restrict__ residual, float* __restrict__ out,
+                      int64_t ss_off, const float* residual, float* out,   // y / residual / out may alias (in-place forms): no restrict
                       int64_t rows_per_sample, int C, int groups, float eps, int64_t rows_per_cta) {
   extern __shared__ __align__(16) float sm[];  // [6][C]: a, o, s1, sh  (per-channel affine after folding mean/rstd)
   float* s_mul = sm;
@@ -131,8 +131,8 @@ groupnorm_silu_kernel(const float* __restrict__ y, const double* __restrict__ st
 // one warp per row; two-pass moments in registers (matches torch.var(unbiased=False) / torch.mean)
 template <int MAXV>
 __global__ void __launch_bounds__(256)
-layernorm_channels_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ residual,
-                          float* __restrict__ out, int64_t rows, int C, float eps, int use_rsqrt) {
+layernorm_channels_kernel(const float* x, const float* __restrict__ gamma, const float* residual,
+                          float* out, int64_t rows, int C, float eps, int use_rsqrt) {   // x / residual / out may alias
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;

@@ -48,8 +48,12 @@ template <bool DDIM, int VEC>
 __global__ void __launch_bounds__(256)
 guided_step_kernel(const float* x, const float* __restrict__ eps_joint, const float* __restrict__ eps_w,
                    const float* __restrict__ noise, const float* __restrict__ init, const float* __restrict__ g_user,
-                   int stock, const dpc_step_coefs k, const StepGeom gm, float* x_out,
+                   int stock, const dpc_step_coefs k_host, const dpc_step_coefs* __restrict__ k_dev, const StepGeom gm, float* x_out,
                    float* __restrict__ x_start_out, int64_t nvec) {
+  // k_dev != NULL: the step's coefficients live in device memory (written by sampler_prepare_kernel inside a captured CUDA
+  // graph, so one graph serves every step of the schedule); the noise operand is then gated by the coefficients themselves
+  const dpc_step_coefs k = k_dev ? *k_dev : k_host;
+  if (k_dev && (DDIM ? k.last != 0 : k.add_noise == 0)) noise = nullptr;
   const int hwv = gm.HW / VEC;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const int pv = (int)(i % hwv);
@@ -133,14 +137,29 @@ predict_x_start_kernel(const float* __restrict__ x, const float* __restrict__ ep
   }
 }
 
+// sidx is a device-side step counter: tt[0..B) <- t_table[*sidx], *cur <- c_table[*sidx], then *sidx += 1 (one thread block)
+__global__ void sampler_prepare_kernel(const int64_t* __restrict__ t_table, const dpc_step_coefs* __restrict__ c_table,
+                                       int32_t* sidx, int32_t nsteps, int64_t* __restrict__ tt, int B, dpc_step_coefs* cur) {
+  int i = *sidx;
+  if (i >= nsteps) i = nsteps - 1;             // replaying past the schedule repeats its last step instead of reading out of bounds
+  const int64_t t = t_table[i];
+  for (int b = threadIdx.x; b < B; b += blockDim.x) tt[b] = t;
+  __syncthreads();                              // every thread has read *sidx before it moves
+  if (threadIdx.x == 0) {
+    *cur = c_table[i];
+    *sidx = i + 1;
+  }
+}
+
 template <bool DDIM>
 static int launch_step(const float* x, const float* eps_joint, const float* eps_w, const float* noise, const float* init,
                        const float* g, int stock, const dpc_step_coefs* coefs, float* x_out, float* x_start_out, int B,
-                       int F, int H, int W, void* stream) {
+                       int F, int H, int W, void* stream, const dpc_step_coefs* coefs_dev = nullptr) {
   DPC_CHECK_ARG(x && eps_joint && eps_w && coefs && x_out && B > 0 && F > 0 && H > 0 && W > 0);
   DPC_CHECK_ARG(stock || g != nullptr);
-  if (!DDIM) DPC_CHECK_ARG(!coefs->add_noise || noise != nullptr);
-  if (DDIM) DPC_CHECK_ARG(coefs->last || noise != nullptr);
+  if (coefs_dev) DPC_CHECK_ARG(noise != nullptr);
+  else if (!DDIM) DPC_CHECK_ARG(!coefs->add_noise || noise != nullptr);
+  else DPC_CHECK_ARG(coefs->last || noise != nullptr);
   StepGeom gm;
   gm.F = F;
   gm.HW = H * W;
@@ -154,14 +173,16 @@ static int launch_step(const float* x, const float* eps_joint, const float* eps_
   if (blocks > cap) blocks = cap;
   cudaStream_t st = (cudaStream_t)stream;
   const float* nz = noise;
-  if (!DDIM && !coefs->add_noise) nz = nullptr;
-  if (DDIM && coefs->last) nz = nullptr;
+  if (!coefs_dev) {
+    if (!DDIM && !coefs->add_noise) nz = nullptr;
+    if (DDIM && coefs->last) nz = nullptr;
+  }
   if (vec)
-    guided_step_kernel<DDIM, 4><<<(unsigned)blocks, 256, 0, st>>>(x, eps_joint, eps_w, nz, init, g, stock, *coefs, gm, x_out,
-                                                                  x_start_out, nvec);
+    guided_step_kernel<DDIM, 4><<<(unsigned)blocks, 256, 0, st>>>(x, eps_joint, eps_w, nz, init, g, stock, *coefs, coefs_dev, gm,
+                                                                  x_out, x_start_out, nvec);
   else
-    guided_step_kernel<DDIM, 1><<<(unsigned)blocks, 256, 0, st>>>(x, eps_joint, eps_w, nz, init, g, stock, *coefs, gm, x_out,
-                                                                  x_start_out, nvec);
+    guided_step_kernel<DDIM, 1><<<(unsigned)blocks, 256, 0, st>>>(x, eps_joint, eps_w, nz, init, g, stock, *coefs, coefs_dev, gm,
+                                                                  x_out, x_start_out, nvec);
   DPC_LAUNCH_CHECK();
   return 0;
 }
@@ -182,6 +203,26 @@ extern "C" int dpc_ddim_guided_step(const float* x, const float* eps_joint, cons
                                     int32_t H, int32_t W, void* stream) {
   return dpc::launch_step<true>(x, eps_joint, eps_w, noise, init, g, use_stock_guidance, coefs, x_out, x_start_out, B, F, H,
                                 W, stream);
+}
+
+extern "C" int dpc_sampler_prepare(const int64_t* t_table, const dpc_step_coefs* c_table, int32_t* step_index, int32_t nsteps,
+                                   int64_t* tt, int32_t B, dpc_step_coefs* cur, void* stream) {
+  using namespace dpc;
+  DPC_CHECK_ARG(t_table && c_table && step_index && tt && cur && nsteps > 0 && B > 0);
+  sampler_prepare_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(t_table, c_table, step_index, nsteps, tt, B, cur);
+  DPC_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int dpc_guided_step_dev(int32_t ddim, const float* x, const float* eps_joint, const float* eps_w, const float* noise,
+                                   const float* init, const dpc_step_coefs* coefs_host, const dpc_step_coefs* coefs_dev,
+                                   float* x_out, float* x_start_out, int32_t B, int32_t F, int32_t H, int32_t W, void* stream) {
+  DPC_CHECK_ARG(coefs_dev != nullptr);
+  if (ddim)
+    return dpc::launch_step<true>(x, eps_joint, eps_w, noise, init, nullptr, 1, coefs_host, x_out, x_start_out, B, F, H, W, stream,
+                                  coefs_dev);
+  return dpc::launch_step<false>(x, eps_joint, eps_w, noise, init, nullptr, 1, coefs_host, x_out, x_start_out, B, F, H, W, stream,
+                                 coefs_dev);
 }
 
 extern "C" int dpc_predict_x_start(const float* x, const float* eps, float sqrt_recip, float sqrt_recipm1, int32_t clip,

@@ -25,7 +25,9 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import _lib
+from .trainer_shim import JellyfishTrainer as Trainer  # noqa: F401  (load-only stand-in, see trainer_shim.py)
 from .diffusion_2d_smoke import cosine_beta_schedule, linear_beta_schedule, sigmoid_beta_schedule
+from .jellyfish_nets import ForceUnet, JellyfishGuidance, Unet  # noqa: F401  (jf.py:276-481: same import surface as the reference module)
 
 ModelPrediction = namedtuple('ModelPrediction', ['pred_noise', 'pred_noise_w', 'pred_x_start'])
 

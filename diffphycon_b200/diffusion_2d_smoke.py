@@ -17,6 +17,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from . import _lib
+from .trainer_shim import SmokeTrainer as Trainer  # noqa: F401  (load-only stand-in, see trainer_shim.py)
 
 ModelPrediction = namedtuple('ModelPrediction', ['pred_noise', 'pred_x_start'])
 
@@ -71,7 +72,15 @@ class StockSmokeGuidance:
 
 
 class GaussianDiffusion(nn.Module):
-    """Constructor: smoke.py:452-472."""
+    """Constructor: smoke.py:452-472.
+
+    Scope: the SAMPLING surface of the reference class (schedules / registered buffers, sample, p_sample_loop, ddim_sample,
+    p_sample).  The training-side methods (forward, p_losses, q_sample; smoke.py:791-839) are not provided: calling the module
+    raises, so a reference training script fails at once instead of at backward()."""
+
+    def forward(self, *a, **k):
+        raise NotImplementedError("diffphycon_b200.GaussianDiffusion is a sampling engine (sample / p_sample_loop / ddim_sample); "
+                                  "training (forward / p_losses / q_sample, smoke.py:791-839) stays with the reference class")
 
     def __init__(self, model, *, image_size, frames, timesteps=1000, sampling_timesteps=None, loss_type='l1',
                  objective='pred_noise', beta_schedule='sigmoid', schedule_fn_kwargs=dict(), ddim_sampling_eta=0.,
@@ -138,6 +147,14 @@ class GaussianDiffusion(nn.Module):
             register_buffer('loss_weight', clipped / (snr + 1))
         self.progress = False      # tqdm bar like the reference's (smoke.py:717) when True
         self._host_sched = None    # CPU copies of the schedule buffers: per-step scalars without device syncs
+        # Step orchestration: with use_cuda_graph one denoising step (time-table lookup, both U-Nets, noise
+        # draw, fused update) is captured ONCE in a CUDA graph and replayed for the whole schedule — one graph launch per step
+        # instead of ~270 kernel launches through Python/ctypes; two_streams runs the two U-Nets on two captured streams
+        # (None = automatic: batches of <= 16 trajectories, where one network alone does not fill the GPU's tail waves).
+        # Only the stock guidance (StockSmokeGuidance) is graph-capturable; other design_fn callables use the eager loop.
+        self.use_cuda_graph = False
+        self.two_streams = None
+        self._graphs = {}
 
     # ---- host-side scalar schedule ------------------------------------------------------------------------------
     def _sched(self):
@@ -230,6 +247,8 @@ class GaussianDiffusion(nn.Module):
         assert init is not None
         init = init.to(device).float().contiguous()
         x[:, 0, 0] = init
+        if self.use_cuda_graph and isinstance(design_fn, StockSmokeGuidance) and not self.progress and x.is_cuda:
+            return self._graph_loop(x, init, design_fn, design_guidance, ddim=False)
         steps = reversed(range(0, self.num_timesteps))
         if self.progress:
             from tqdm.auto import tqdm
@@ -253,6 +272,8 @@ class GaussianDiffusion(nn.Module):
         img = self.sample_noise(list(shape), device)
         init = init.to(device).float().contiguous()
         img[:, 0, 0] = init
+        if self.use_cuda_graph and isinstance(design_fn, StockSmokeGuidance) and not self.progress and img.is_cuda:
+            return self._graph_loop(img, init, design_fn, design_guidance, ddim=True)
         it = time_pairs
         if self.progress:
             from tqdm.auto import tqdm
@@ -291,6 +312,58 @@ class GaussianDiffusion(nn.Module):
         _lib.guided_step(True, img.contiguous(), eps_j, eps_w, noise, init, g, c, out, None, b, f, h, w)
         return out
 
+    # ---- CUDA-graph step orchestration ---------------------------------------------------------------------------------
+    def _step_tables(self, design_fn, design_guidance, ddim):
+        """Per-step (time, coefficients) of the whole schedule, in sampling order, exactly as p_sample / ddim_step set them."""
+        s = self._sched()
+        ts, cs = [], []
+        if not ddim:
+            for t in reversed(range(0, self.num_timesteps)):
+                c = self._coefs(t, design_fn, design_guidance)
+                c.posterior_mean_coef1 = float(s['posterior_mean_coef1'][t])
+                c.posterior_mean_coef2 = float(s['posterior_mean_coef2'][t])
+                c.sigma = float((0.5 * s['posterior_log_variance_clipped'][t]).exp())
+                c.add_noise = 1 if t > 0 else 0
+                ts.append(t)
+                cs.append(c)
+        else:
+            times = torch.linspace(-1, self.num_timesteps - 1, steps=self.sampling_timesteps + 1)
+            times = list(reversed(times.int().tolist()))
+            eta = self.ddim_sampling_eta
+            for time, time_next in zip(times[:-1], times[1:]):
+                c = self._coefs(time, design_fn, design_guidance)
+                if time_next < 0:
+                    c.last = 1
+                else:
+                    alpha, alpha_next = s['alphas_cumprod'][time], s['alphas_cumprod'][time_next]
+                    sigma = eta * ((1 - alpha / alpha_next) * (1 - alpha_next) / (1 - alpha)).sqrt()
+                    cc = (1 - alpha_next - sigma ** 2).sqrt()
+                    c.sqrt_alpha_next, c.c, c.ddim_sigma, c.last = float(alpha_next.sqrt()), float(cc), float(sigma), 0
+                ts.append(time)
+                cs.append(c)
+        return ts, cs
+
+    def _graph_loop(self, x, init, design_fn, design_guidance, ddim):
+        """The whole sampling loop as replays of one captured step.  Same arithmetic, same kernels and the same torch.randn
+        draws as the eager loop (the final step draws a noise tensor it does not use)."""
+        import ctypes
+        dev = x.device
+        shape = tuple(x.shape)
+        b = shape[0]
+        two = self.two_streams if self.two_streams is not None else b <= 16
+        ts, cs = self._step_tables(design_fn, design_guidance, ddim)
+        n = len(ts)
+        csize = ctypes.sizeof(_lib.StepCoefs)
+        raw = b"".join(bytes(c) for c in cs)
+        key = (shape, str(dev), ddim, two, design_guidance, hash(raw), tuple(ts), getattr(self, "_noise_key", None),
+               self.model_joint._param_key(), self.model_thetas._param_key())
+        g = self._graphs.get(key)
+        if g is None:
+            self._graphs.clear()       # one captured schedule at a time: a graph pins its activation buffers
+            g = _GraphedStep(self, shape, dev, ddim, two, ts, raw, csize, cs[0])
+            self._graphs[key] = g
+        return g.run(x, init, n)
+
     @torch.no_grad()
     def sample(self, batch_size=16, design_fn=None, design_guidance="standard", init=None, init_u=None, control=None,
                low=None, device=None):
@@ -300,3 +373,64 @@ class GaussianDiffusion(nn.Module):
         size = (batch_size, self.frames, self.channels, self.image_size, self.image_size)
         return sample_fn(size, design_fn, design_guidance, init=init, init_u=init_u, control=control, low=low,
                          device=device)
+
+
+class _GraphedStep:
+    """One denoising step captured in a CUDA graph: dpc_sampler_prepare (device-side step counter -> time tensor and step
+    coefficients), joint and prior U-Net forwards (optionally on two streams), torch.randn, dpc_guided_step_dev in place."""
+
+    def __init__(self, diff, shape, dev, ddim, two_streams, ts, raw_coefs, csize, coefs_host):
+        self.diff, self.shape, self.ddim, self.two = diff, shape, ddim, two_streams
+        b, f, c, h, w = shape
+        self.n = len(ts)
+        self.x = torch.randn(shape, device=dev)
+        self.init = torch.zeros(b, h, w, device=dev)
+        self.tt = torch.zeros(b, dtype=torch.long, device=dev)
+        self.sidx = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.cur = torch.zeros(csize, dtype=torch.uint8, device=dev)
+        self.t_table = torch.tensor(ts, dtype=torch.long, device=dev)
+        self.c_table = torch.frombuffer(bytearray(raw_coefs), dtype=torch.uint8).to(dev)
+        self.eps_w = torch.empty(b, f, diff.model_thetas.out_dim, h, w, device=dev)
+        self.coefs_host = coefs_host
+        self.stream = torch.cuda.Stream(device=dev)
+        self.side = torch.cuda.Stream(device=dev) if two_streams else None
+        cur_stream = torch.cuda.current_stream(dev)
+        self.stream.wait_stream(cur_stream)
+        with torch.cuda.stream(self.stream):          # warm-up on the capture stream: packs weights, fills the buffer pools
+            for _ in range(2):
+                self._body()
+        cur_stream.wait_stream(self.stream)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        c0 = _lib.LaunchCounter.count
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            self._body()
+        self.kernels_per_replay = _lib.LaunchCounter.count - c0     # launches of this binding captured in the graph
+
+    def _body(self):
+        d = self.diff
+        b, f, c, h, w = self.shape
+        _lib.sampler_prepare(self.t_table, self.c_table, self.sidx, self.n, self.tt, b, self.cur)
+        if self.side is not None:
+            main = torch.cuda.current_stream()
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                d.model_thetas.forward_slice(self.x, 3, self.tt, self.eps_w)
+            eps_j = d.model_joint(self.x, self.tt)
+            main.wait_stream(self.side)
+        else:
+            eps_j = d.model_joint(self.x, self.tt)
+            d.model_thetas.forward_slice(self.x, 3, self.tt, self.eps_w)
+        noise = d.sample_noise(list(self.shape), self.x.device)    # captured: torch.randn (or the sharded global-noise slice)
+        _lib.guided_step_dev(self.ddim, self.x, eps_j, self.eps_w, noise, self.init, self.coefs_host, self.cur, self.x, None,
+                             b, f, h, w)
+
+    def run(self, x0, init, nsteps):
+        self.x.copy_(x0)
+        self.init.copy_(init)
+        self.sidx.zero_()
+        for _ in range(nsteps):
+            self.graph.replay()
+            _lib.LaunchCounter.graph_launches += 1
+            _lib.LaunchCounter.count += self.kernels_per_replay
+        return self.x.clone()

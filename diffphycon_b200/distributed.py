@@ -34,10 +34,12 @@ class _GlobalNoise:
             full = self.orig([self.bg, *shape[1:]], device)
             return full[self.lo:self.hi].contiguous()
         self.d.sample_noise = sample_noise
+        self.d._noise_key = (self.bg, self.lo, self.hi)     # part of the CUDA-graph cache key (the noise draw is captured)
         return self
 
     def __exit__(self, *a):
         self.d.sample_noise = self.orig
+        self.d._noise_key = None
 
 
 @torch.no_grad()

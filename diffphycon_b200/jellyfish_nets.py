@@ -135,9 +135,9 @@ class _Net2D(nn.Module):
         self._packed = None
         self._packed_key = None
 
-    def _load_from_state_dict(self, *a, **k):
+    def load_state_dict(self, *a, **k):
         self.invalidate_packed()
-        return super()._load_from_state_dict(*a, **k)
+        return super().load_state_dict(*a, **k)
 
     def _apply(self, fn, *a, **k):
         self.invalidate_packed()

@@ -157,8 +157,32 @@ class _Pool:
         self.free.setdefault((t.numel(), t.dtype), []).append(t)
 
 
+def pool_for(device) -> _Pool:
+    """The scratch-buffer pool of (device, current stream).  Buffers are recycled in launch order on ONE stream, so a pool is
+    never shared between streams: two models sampled concurrently on different streams get disjoint scratch memory."""
+    device = torch.device(device)
+    stream = torch.cuda.current_stream(device).cuda_stream if device.type == "cuda" else 0
+    key = (device, stream)
+    p = Unet3D_with_Conv3D._pools.get(key)
+    if p is None:
+        p = Unet3D_with_Conv3D._pools[key] = _Pool(device)
+    return p
+
+
+def release_pool(device=None):
+    """Drop the cached scratch buffers (of one device, or all): the pool otherwise keeps the peak activation memory of the
+    largest batch it has served for the life of the process."""
+    for key in list(Unet3D_with_Conv3D._pools):
+        if device is None or key[0] == torch.device(device):
+            del Unet3D_with_Conv3D._pools[key]
+
+
 class Unet3D_with_Conv3D(nn.Module):
-    """See module docstring.  Constructor signature: conv3d.py:357-372."""
+    """See module docstring.  Constructor signature: conv3d.py:357-372.
+
+    Scope: the SAMPLING surface of the reference class (forward under no_grad, the engine's kernels have no backward for this
+    network).  Calling forward with autograd enabled on inputs / parameters that require grad raises — a reference training
+    script must keep using the reference module."""
 
     def __init__(self, dim, cond_dim=None, out_dim=None, dim_mults=(1, 2, 4, 8), channels=6, attn_heads=4,
                  attn_dim_head=32, use_bert_text_cond=False, init_dim=None, init_kernel_size=7,
@@ -234,6 +258,7 @@ class Unet3D_with_Conv3D(nn.Module):
         # "3xtf32": error-compensated split products on the generic kernel, near-fp32 (parity / debugging mode)
         self.precision = "tf32"
         self.micro_batch: Optional[int] = None  # samples per pass through the network (None = whole batch)
+        self.paranoid_weight_check = False      # fingerprint the weights every forward (see invalidate_packed)
         self._packed = None
         self._packed_key = None
         self._geo_cache: Dict[tuple, dict] = {}
@@ -252,7 +277,30 @@ class Unet3D_with_Conv3D(nn.Module):
         return out
 
     def _param_key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self.paranoid_weight_check:
+            # content fingerprint (one multi-tensor launch + one device->host read per forward): catches in-place edits through
+            # `.data`, which neither move the storage nor bump the version counter
+            norms = torch._foreach_norm([p.detach() for p in self.parameters()])
+            key += (tuple(torch.stack(norms).double().cpu().tolist()),)
+        return key
+
+    def invalidate_packed(self):
+        """Drop the packed weight copies (TF32-rounded K-major matrices, folded LayerNorm gains, position-bias tables).
+        They are rebuilt automatically when a parameter is replaced or modified through autograd-visible in-place ops, by
+        load_state_dict() and by .to()/.cuda(); call this after editing weights through `.data` (e.g. `p.data.copy_(...)`,
+        ema_pytorch-style updates), which PyTorch does not version — or set `paranoid_weight_check = True`."""
+        self._packed = None
+        self._packed_key = None
+        self._geo_cache.clear()
+
+    def _load_from_state_dict(self, *a, **k):
+        self.invalidate_packed()
+        return super()._load_from_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate_packed()
+        return super()._apply(fn, *a, **k)
 
     def _ensure_packed(self, device):
         assert self.precision in ("tf32", "3xtf32")
@@ -383,13 +431,23 @@ class Unet3D_with_Conv3D(nn.Module):
         self._geo_cache[key] = g
         return g
 
+    def load_state_dict(self, *a, **k):
+        self.invalidate_packed()
+        return super().load_state_dict(*a, **k)
+
     # ------------------------------------------------------------------------------------------------------------
     # forward
     # ------------------------------------------------------------------------------------------------------------
+    def forward(self, x, time, cond=None, null_cond_prob=0., focus_present_mask=None, prob_focus_present=0.):
+        """conv3d.py:486-552.  x: [B,F,C,H,W] fp32 CUDA, time: [B] -> [B,F,out_dim,H,W].  Sampling only (no autograd)."""
+        if torch.is_grad_enabled() and x.requires_grad:
+            raise RuntimeError("diffphycon_b200.Unet3D_with_Conv3D is a sampling engine: its kernels have no backward pass, "
+                               "so an input that requires grad cannot be differentiated through it")
+        return self._forward_nograd(x, time, cond, null_cond_prob, focus_present_mask, prob_focus_present)
+
     @torch.no_grad()
     @_lib.device_guarded
-    def forward(self, x, time, cond=None, null_cond_prob=0., focus_present_mask=None, prob_focus_present=0.):
-        """conv3d.py:486-552.  x: [B,F,C,H,W] fp32 CUDA, time: [B] -> [B,F,out_dim,H,W]."""
+    def _forward_nograd(self, x, time, cond=None, null_cond_prob=0., focus_present_mask=None, prob_focus_present=0.):
         _require_cuda(x)
         if cond is not None:
             raise NotImplementedError("cond is unused on the DiffPhyCon path")
@@ -425,13 +483,10 @@ class Unet3D_with_Conv3D(nn.Module):
             self._forward_chunk(x_full[b0:b1], time[b0:b1], out[b0:b1], c0, x_full.shape[2])
         return out
 
-    _pools: Dict[torch.device, _Pool] = {}   # one buffer pool per device, shared by every network instance
+    _pools: Dict[tuple, _Pool] = {}   # one buffer pool per (device, stream), shared by every network instance
 
     def _pool(self, device) -> _Pool:
-        p = Unet3D_with_Conv3D._pools.get(device)
-        if p is None:
-            p = Unet3D_with_Conv3D._pools[device] = _Pool(device)
-        return p
+        return pool_for(device)
 
     def _forward_chunk(self, x, time, out, c0, ctot):
         P = self._packed

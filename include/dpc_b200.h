@@ -225,6 +225,17 @@ int dpc_ddim_guided_step(const float* x, const float* eps_joint, const float* ep
                          const float* init, const float* g, int32_t use_stock_guidance,
                          const dpc_step_coefs* coefs, float* x_out, float* x_start_out,
                          int32_t B, int32_t F, int32_t H, int32_t W, void* stream);
+/* Table-driven form of the two entry points above for a step captured ONCE in a CUDA graph and replayed for the whole
+ * schedule: dpc_sampler_prepare reads the device-side step counter *step_index, writes the batched time
+ * tensor tt[0..B) = t_table[i] (the U-Nets' `time` argument) and *cur = c_table[i], then increments the counter;
+ * dpc_guided_step_dev is dpc_ddpm/ddim_guided_step with the stock guidance, taking the per-step coefficients from device
+ * memory (`coefs_dev` = cur).  `coefs_host` supplies what does not change from step to step (w_energy, rescaler).  `noise` must
+ * be non-NULL; it is ignored when the step's coefficients say so (add_noise == 0 / last != 0).  x_out may alias x. */
+int dpc_sampler_prepare(const int64_t* t_table, const dpc_step_coefs* c_table, int32_t* step_index, int32_t nsteps, int64_t* tt,
+                        int32_t B, dpc_step_coefs* cur, void* stream);
+int dpc_guided_step_dev(int32_t ddim, const float* x, const float* eps_joint, const float* eps_w, const float* noise,
+                        const float* init, const dpc_step_coefs* coefs_host, const dpc_step_coefs* coefs_dev, float* x_out,
+                        float* x_start_out, int32_t B, int32_t F, int32_t H, int32_t W, void* stream);
 /* x_start = maybe_clip(sqrt_recip*x - sqrt_recipm1*eps) — smoke.py:576-580, :620-621; for user design_fn callables. */
 int dpc_predict_x_start(const float* x, const float* eps, float sqrt_recip, float sqrt_recipm1, int32_t clip,
                         float* x_start, int64_t n, void* stream);
