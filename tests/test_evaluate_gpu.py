@@ -1,5 +1,7 @@
-"""Evaluation stage (diffphycon_b200/evaluate.py, dpc_smoke_eval_sums) against a line-by-line torch restatement of
-InferencePipeline.multi_evaluate's metric block (inference/inference_2d_smoke.py:384-416) applied to the same rollout outputs."""
+"""Evaluation stage (diffphycon_b200/evaluate.py, dpc_smoke_eval_sums): (1) pinned to the UNMODIFIED reference method
+(InferencePipeline.multi_evaluate lifted with ast and run with the reference's own solver, tests/golden/multi_evaluate.npz), and
+(2) per-trajectory metrics against a line-by-line torch restatement of the metric block (inference/inference_2d_smoke.py:384-416)
+applied to the same rollout outputs."""
 import numpy as np
 import pytest
 import torch
@@ -63,3 +65,20 @@ def test_multi_evaluate_matches_reference_metric_block():
     for k, v in ref.items():
         assert np.allclose(res[k], v, rtol=1e-6, atol=1e-9), (k, res[k], v)   # the restatement sums pred in fp32 where the kernel uses fp64
     assert np.allclose(res["means"][0], ref["J_total"].mean()) and np.allclose(res["means"][4], ref["n_l2"].mean())
+
+
+@pytest.mark.parametrize("B", [1, 2])
+def test_multi_evaluate_matches_unmodified_reference(B, golden_dir):
+    """The whole evaluation stage — re-imposed initial density, indirect-control window, 256-frame rollout of every trajectory,
+    metric block — against the values the UNMODIFIED `InferencePipeline.multi_evaluate` returned for the same seeded inputs
+    (tests/golden/make_golden_multi_evaluate.py: the method lifted from inference/inference_2d_smoke.py:299-427 with ast,
+    executed with the reference's own solver / phi).  Relative tolerance 2e-5: fp64 rollout (1e-8 class), fp32 densities."""
+    import os
+    from tests.multi_evaluate_fixture import inputs
+    z = np.load(os.path.join(golden_dir, "multi_evaluate.npz"))
+    pred, data = inputs(B)
+    res = ev.multi_evaluate(pred.cuda(), data.cuda(), w_energy=float(z["w_energy"]), per_timelength=256)
+    for i, name in enumerate(("J_total", "J_target", "J_energy", "mse", "n_l2")):
+        ref = float(z[f"b{B}/{name}"][0])
+        got = float(res["means"][i][0])
+        assert abs(got - ref) <= 2e-5 * max(abs(ref), 1e-3), (name, got, ref)
