@@ -11,135 +11,7 @@ constexpr int DH = 32;
 constexpr float ATT_SCALE = 0.17677669529663687f;  // 32 ** -0.5 (conv3d.py:286)
 
 // ------------------------------------------------------------------------------------------------------------
-// temporal attention: one warp per (sample, pixel, head); lane i owns query frame(s) i (+32).
-// K and V of all frames live in shared memory (row stride 36 floats: conflict-free float4 stores per quarter-warp,
-// broadcast float4 reads).  Warp shuffles are not needed: every lane runs its own softmax row.
-// ------------------------------------------------------------------------------------------------------------
-template <int R>  // query rows per lane: F <= 32*R
-__global__ void __launch_bounds__(128)
-temporal_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ rope_cos,
-                          const float* __restrict__ rope_sin, const float* __restrict__ pos_bias,
-                          float* __restrict__ out, int64_t total_warps, int F, int HW, int heads, int use_rope) {
-  extern __shared__ __align__(16) float sm[];
-  constexpr int LD = DH + 4;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int FP = 32 * R;
-  float* Ks = sm + (size_t)warp * 2 * FP * LD;
-  float* Vs = Ks + FP * LD;
-  const int C3 = 3 * heads * DH;
-  const int hid = heads * DH;
-
-  for (int64_t wg = (int64_t)blockIdx.x * 4 + warp; wg < total_warps; wg += (int64_t)gridDim.x * 4) {
-    const int head = (int)(wg % heads);
-    const int64_t bp = wg / heads;
-    const int pix = (int)(bp % HW);
-    const int64_t b = bp / HW;
-
-    float q[R][DH];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int f = lane + 32 * r;
-      if (f < F) {
-        const float* row = qkv + (((size_t)b * F + f) * HW + pix) * C3 + head * DH;
-        float kk[DH], vv[DH];
-#pragma unroll
-        for (int c = 0; c < DH; c += 4) {
-          float4 a = __ldcs(reinterpret_cast<const float4*>(row + c));
-          float4 k4 = __ldcs(reinterpret_cast<const float4*>(row + hid + c));
-          float4 v4 = __ldcs(reinterpret_cast<const float4*>(row + 2 * hid + c));
-          q[r][c] = __fmul_rn(a.x, ATT_SCALE); q[r][c + 1] = __fmul_rn(a.y, ATT_SCALE);
-          q[r][c + 2] = __fmul_rn(a.z, ATT_SCALE); q[r][c + 3] = __fmul_rn(a.w, ATT_SCALE);
-          kk[c] = k4.x; kk[c + 1] = k4.y; kk[c + 2] = k4.z; kk[c + 3] = k4.w;
-          vv[c] = v4.x; vv[c + 1] = v4.y; vv[c + 2] = v4.z; vv[c + 3] = v4.w;
-        }
-        if (use_rope) {
-          const float* cs = rope_cos + (size_t)f * DH;
-          const float* sn = rope_sin + (size_t)f * DH;
-#pragma unroll
-          for (int c = 0; c < DH; c += 2) {
-            const float c0 = __ldg(cs + c), s0 = __ldg(sn + c), c1 = __ldg(cs + c + 1), s1 = __ldg(sn + c + 1);
-            // t*cos + rotate_half(t)*sin with rotate_half: (x0, x1) -> (-x1, x0)
-            float q0 = q[r][c], q1 = q[r][c + 1];
-            q[r][c] = __fadd_rn(__fmul_rn(q0, c0), __fmul_rn(-q1, s0));
-            q[r][c + 1] = __fadd_rn(__fmul_rn(q1, c1), __fmul_rn(q0, s1));
-            float k0 = kk[c], k1 = kk[c + 1];
-            kk[c] = __fadd_rn(__fmul_rn(k0, c0), __fmul_rn(-k1, s0));
-            kk[c + 1] = __fadd_rn(__fmul_rn(k1, c1), __fmul_rn(k0, s1));
-          }
-        }
-#pragma unroll
-        for (int c = 0; c < DH; c += 4) {
-          *reinterpret_cast<float4*>(Ks + f * LD + c) = make_float4(kk[c], kk[c + 1], kk[c + 2], kk[c + 3]);
-          *reinterpret_cast<float4*>(Vs + f * LD + c) = make_float4(vv[c], vv[c + 1], vv[c + 2], vv[c + 3]);
-        }
-      }
-    }
-    __syncwarp();
-
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int i = lane + 32 * r;
-      if (i < F) {
-        float s[32 * R];
-        float mx = -INFINITY;
-        const float* brow = pos_bias ? pos_bias + ((size_t)head * F + i) * F : nullptr;
-#pragma unroll
-        for (int j = 0; j < 32 * R; ++j) {
-          if (j < F) {
-            // four independent partial sums: a 32-long dependent FMA chain would expose the 4-cycle FMA latency
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-            for (int c = 0; c < DH; c += 4) {
-              float4 k4 = *reinterpret_cast<const float4*>(Ks + j * LD + c);
-              a0 = fmaf(q[r][c], k4.x, a0);
-              a1 = fmaf(q[r][c + 1], k4.y, a1);
-              a2 = fmaf(q[r][c + 2], k4.z, a2);
-              a3 = fmaf(q[r][c + 3], k4.w, a3);
-            }
-            float acc = (a0 + a1) + (a2 + a3);
-            if (brow) acc += __ldg(brow + j);
-            s[j] = acc;
-            mx = fmaxf(mx, acc);
-          }
-        }
-        float l = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32 * R; ++j) {
-          if (j < F) {
-            s[j] = expf(s[j] - mx);
-            l += s[j];
-          }
-        }
-        const float inv = 1.0f / l;
-        float o[DH];
-#pragma unroll
-        for (int c = 0; c < DH; ++c) o[c] = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32 * R; ++j) {
-          if (j < F) {
-            const float pj = s[j] * inv;
-#pragma unroll
-            for (int c = 0; c < DH; c += 4) {
-              float4 v4 = *reinterpret_cast<const float4*>(Vs + j * LD + c);
-              o[c] = fmaf(pj, v4.x, o[c]);
-              o[c + 1] = fmaf(pj, v4.y, o[c + 1]);
-              o[c + 2] = fmaf(pj, v4.z, o[c + 2]);
-              o[c + 3] = fmaf(pj, v4.w, o[c + 3]);
-            }
-          }
-        }
-        float* orow = out + (((size_t)b * F + i) * HW + pix) * hid + head * DH;
-#pragma unroll
-        for (int c = 0; c < DH; c += 4)
-          *reinterpret_cast<float4*>(orow + c) = make_float4(o[c], o[c + 1], o[c + 2], o[c + 3]);
-      }
-    }
-    __syncwarp();
-  }
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// temporal attention, F <= 32, tensor-core version: one warp per (sample, pixel, head).
+// temporal attention, F <= 64, tensor-core version: one warp per (sample, pixel, head); 32 queries at a time against all keys.
 //   stage : coalesced 128-byte row segments of q|k|v -> scale, RoPE -> shared memory (row stride 36 floats)
 //   S     : Q K^T as 2x4 m16n8k8 TF32 MMAs per k-step (ldmatrix fragments), + relative bias, key mask, row softmax
 //           (row reductions stay inside a quad: 2 shuffles)
@@ -181,17 +53,18 @@ __device__ __forceinline__ void mma_op(float (&d)[4], const float (&a)[4], float
   }
 }
 
-template <bool PRECISE>
+template <bool PRECISE, int NF>   // NF = 32 or 64: frames padded to a multiple of 32 (F <= NF)
 __global__ void __launch_bounds__(128)
 temporal_attention_mma_kernel(const float* __restrict__ qkv, const float* __restrict__ rope_cos,
                               const float* __restrict__ rope_sin, const float* __restrict__ pos_bias,
                               float* __restrict__ out, int64_t total_warps, int F, int HW, int heads, int use_rope) {
   extern __shared__ __align__(16) float sm[];
   constexpr int LD = DH + 4;
+  constexpr int NKT = NF / 8;                         // key blocks of 8
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  float* Qs = sm + (size_t)warp * 3 * 32 * LD;
-  float* Ks = Qs + 32 * LD;
-  float* Vs = Ks + 32 * LD;
+  float* Qs = sm + (size_t)warp * 3 * NF * LD;
+  float* Ks = Qs + NF * LD;
+  float* Vs = Ks + NF * LD;
   const int C3 = 3 * heads * DH, hid = heads * DH;
   const int g = lane >> 2, t = lane & 3;
   const int lf = lane >> 3, lc = (lane & 7) * 4;      // staging: frame-in-group, first channel of this lane's float4
@@ -203,7 +76,7 @@ temporal_attention_mma_kernel(const float* __restrict__ qkv, const float* __rest
     const int64_t b = bp / HW;
     // ---- stage q, k, v ----
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < NF / 4; ++it) {
       const int f = it * 4 + lf;
       float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f), k4 = q4, v4 = q4;
       if (f < F) {
@@ -235,103 +108,107 @@ temporal_attention_mma_kernel(const float* __restrict__ qkv, const float* __rest
       *reinterpret_cast<float4*>(Vs + f * LD + lc) = v4;
     }
     __syncwarp();
-    // ---- S = Q K^T ----
-    float s[2][4][4];
+#pragma unroll 1
+    for (int qh = 0; qh < NF / 32; ++qh) {             // 32 queries at a time (two m16 tiles) against all NF keys
+      const float* Qh = Qs + qh * 32 * LD;
+      // ---- S = Q K^T ----
+      float s[2][NKT][4];
 #pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
+        for (int nt = 0; nt < NKT; ++nt)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) s[mt][nt][e] = 0.f;
+          for (int e = 0; e < 4; ++e) s[mt][nt][e] = 0.f;
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      float a[2][4];
+      for (int ks = 0; ks < 4; ++ks) {
+        float a[2][4];
 #pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        const float* qa = Qs + (mt * 16 + g) * LD + ks * 8 + t;
-        a[mt][0] = qa[0]; a[mt][1] = qa[8 * LD]; a[mt][2] = qa[4]; a[mt][3] = qa[8 * LD + 4];
+        for (int mt = 0; mt < 2; ++mt) {
+          const float* qa = Qh + (mt * 16 + g) * LD + ks * 8 + t;
+          a[mt][0] = qa[0]; a[mt][1] = qa[8 * LD]; a[mt][2] = qa[4]; a[mt][3] = qa[8 * LD + 4];
+        }
+#pragma unroll
+        for (int nt = 0; nt < NKT; ++nt) {
+          const float* kb = Ks + (nt * 8 + g) * LD + ks * 8 + t;   // B[k = d][n = key] = K[key][d]
+          const float b0 = kb[0], b1 = kb[4];
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) mma_op<PRECISE>(s[mt][nt], a[mt], b0, b1);
+        }
       }
+      // ---- bias, key mask, softmax over keys (row = qh*32 + mt*16 + g + 8*h, col = nt*8 + 2t + e) ----
+      float inv[2][2];
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const float* kb = Ks + (nt * 8 + g) * LD + ks * 8 + t;   // B[k = d][n = key] = K[key][d]
-        const float b0 = kb[0], b1 = kb[4];
+      for (int mt = 0; mt < 2; ++mt)
 #pragma unroll
-        for (int mt = 0; mt < 2; ++mt) mma_op<PRECISE>(s[mt][nt], a[mt], b0, b1);
+        for (int h = 0; h < 2; ++h) {
+          const int row = qh * 32 + mt * 16 + g + 8 * h;
+          const float* brow = (pos_bias && row < F) ? pos_bias + ((size_t)head * F + row) * F : nullptr;
+          float mx = -INFINITY;
+#pragma unroll
+          for (int nt = 0; nt < NKT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int col = nt * 8 + 2 * t + e;
+              float v = s[mt][nt][2 * h + e];
+              if (brow && col < F) v += __ldg(brow + col);
+              if (col >= F) v = -INFINITY;
+              s[mt][nt][2 * h + e] = v;
+              mx = fmaxf(mx, v);
+            }
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          float l = 0.f;
+#pragma unroll
+          for (int nt = 0; nt < NKT; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float pv = expf(s[mt][nt][2 * h + e] - mx);
+              s[mt][nt][2 * h + e] = pv;
+              l += pv;
+            }
+          l += __shfl_xor_sync(0xffffffffu, l, 1);
+          l += __shfl_xor_sync(0xffffffffu, l, 2);
+          inv[mt][h] = 1.0f / l;
+        }
+      // ---- O = P V (k index of the MMA mapped to keys 8*kb + 2t, 8*kb + 2t + 1) ----
+      float o[2][4][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[mt][dn][e] = 0.f;
+#pragma unroll
+      for (int kb = 0; kb < NKT; ++kb) {
+        float a[2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          a[mt][0] = s[mt][kb][0] * inv[mt][0];   // (row g,   key 2t)
+          a[mt][1] = s[mt][kb][2] * inv[mt][1];   // (row g+8, key 2t)
+          a[mt][2] = s[mt][kb][1] * inv[mt][0];   // (row g,   key 2t+1)
+          a[mt][3] = s[mt][kb][3] * inv[mt][1];   // (row g+8, key 2t+1)
+        }
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn) {
+          const float* vb = Vs + (kb * 8 + 2 * t) * LD + dn * 8 + g;
+          const float b0 = vb[0], b1 = vb[LD];
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt) mma_op<PRECISE>(o[mt][dn], a[mt], b0, b1);
+        }
       }
+      __syncwarp();   // every lane is done reading this half of Qs: reuse it as the output staging tile
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int dn = 0; dn < 4; ++dn) {
+          float* od = Qs + (qh * 32 + mt * 16 + g) * LD + dn * 8 + 2 * t;
+          *reinterpret_cast<float2*>(od) = make_float2(o[mt][dn][0], o[mt][dn][1]);
+          *reinterpret_cast<float2*>(od + 8 * LD) = make_float2(o[mt][dn][2], o[mt][dn][3]);
+        }
     }
-    // ---- bias, key mask, softmax over keys (row = mt*16 + g + 8*h, col = nt*8 + 2t + e) ----
-    float inv[2][2];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int row = mt * 16 + g + 8 * h;
-        const float* brow = (pos_bias && row < F) ? pos_bias + ((size_t)head * F + row) * F : nullptr;
-        float mx = -INFINITY;
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int col = nt * 8 + 2 * t + e;
-            float v = s[mt][nt][2 * h + e];
-            if (brow && col < F) v += __ldg(brow + col);
-            if (col >= F) v = -INFINITY;
-            s[mt][nt][2 * h + e] = v;
-            mx = fmaxf(mx, v);
-          }
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-        float l = 0.f;
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const float pv = expf(s[mt][nt][2 * h + e] - mx);
-            s[mt][nt][2 * h + e] = pv;
-            l += pv;
-          }
-        l += __shfl_xor_sync(0xffffffffu, l, 1);
-        l += __shfl_xor_sync(0xffffffffu, l, 2);
-        inv[mt][h] = 1.0f / l;
-      }
-    // ---- O = P V (k index of the MMA mapped to keys 8*kb + 2t, 8*kb + 2t + 1) ----
-    float o[2][4][4];
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int dn = 0; dn < 4; ++dn)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) o[mt][dn][e] = 0.f;
-#pragma unroll
-    for (int kb = 0; kb < 4; ++kb) {
-      float a[2][4];
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt) {
-        a[mt][0] = s[mt][kb][0] * inv[mt][0];   // (row g,   key 2t)
-        a[mt][1] = s[mt][kb][2] * inv[mt][1];   // (row g+8, key 2t)
-        a[mt][2] = s[mt][kb][1] * inv[mt][0];   // (row g,   key 2t+1)
-        a[mt][3] = s[mt][kb][3] * inv[mt][1];   // (row g+8, key 2t+1)
-      }
-#pragma unroll
-      for (int dn = 0; dn < 4; ++dn) {
-        const float* vb = Vs + (kb * 8 + 2 * t) * LD + dn * 8 + g;
-        const float b0 = vb[0], b1 = vb[LD];
-#pragma unroll
-        for (int mt = 0; mt < 2; ++mt) mma_op<PRECISE>(o[mt][dn], a[mt], b0, b1);
-      }
-    }
-    __syncwarp();   // every lane is done reading Qs: reuse it as the output staging tile
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-      for (int dn = 0; dn < 4; ++dn) {
-        float* od = Qs + (mt * 16 + g) * LD + dn * 8 + 2 * t;
-        *reinterpret_cast<float2*>(od) = make_float2(o[mt][dn][0], o[mt][dn][1]);
-        *reinterpret_cast<float2*>(od + 8 * LD) = make_float2(o[mt][dn][2], o[mt][dn][3]);
-      }
     __syncwarp();
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < NF / 4; ++it) {
       const int f = it * 4 + lf;
       if (f < F) {
         const float4 v = *reinterpret_cast<const float4*>(Qs + f * LD + lc);
@@ -747,31 +624,33 @@ extern "C" int dpc_temporal_attention(const float* qkv, const float* rope_cos, c
   const int64_t cap = 148LL * 64;
   if (blocks > cap) blocks = cap;
   cudaStream_t st = (cudaStream_t)stream;
+  // F <= 32 and 32 < F <= 64 both run the tensor-core kernel (frames padded to 32 / 64, padded keys masked)
+  const int NFr = F <= 32 ? 32 : 64;
+  const size_t smem = (size_t)4 * 3 * NFr * 36 * sizeof(float);
+  static bool configured_[kMaxDevices] = {};
+  bool& configured = configured_[device_ordinal()];
+  if (!configured) {
+    const int s32 = 4 * 3 * 32 * 36 * (int)sizeof(float), s64 = 4 * 3 * 64 * 36 * (int)sizeof(float);
+    DPC_CUDA(cudaFuncSetAttribute(temporal_attention_mma_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, s32));
+    DPC_CUDA(cudaFuncSetAttribute(temporal_attention_mma_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, s32));
+    DPC_CUDA(cudaFuncSetAttribute(temporal_attention_mma_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));
+    DPC_CUDA(cudaFuncSetAttribute(temporal_attention_mma_kernel<true, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));
+    configured = true;
+  }
   if (F <= 32) {
-    const size_t smem = (size_t)4 * 3 * 32 * 36 * sizeof(float);
-    static bool configured_[kMaxDevices] = {};
-    bool& configured = configured_[device_ordinal()];
-    if (!configured) {
-      DPC_CUDA(cudaFuncSetAttribute(temporal_attention_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      DPC_CUDA(cudaFuncSetAttribute(temporal_attention_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = true;
-    }
     if (precise)
-      temporal_attention_mma_kernel<true><<<(unsigned)blocks, 128, smem, st>>>(qkv, rope_cos, rope_sin, pos_bias, out, total, F,
-                                                                              HW, heads, use_rope);
+      temporal_attention_mma_kernel<true, 32><<<(unsigned)blocks, 128, smem, st>>>(qkv, rope_cos, rope_sin, pos_bias, out, total, F,
+                                                                                  HW, heads, use_rope);
     else
-      temporal_attention_mma_kernel<false><<<(unsigned)blocks, 128, smem, st>>>(qkv, rope_cos, rope_sin, pos_bias, out, total, F,
-                                                                               HW, heads, use_rope);
+      temporal_attention_mma_kernel<false, 32><<<(unsigned)blocks, 128, smem, st>>>(qkv, rope_cos, rope_sin, pos_bias, out, total, F,
+                                                                                   HW, heads, use_rope);
   } else {
-    const size_t smem = (size_t)4 * 2 * 64 * 36 * sizeof(float);
-    static bool configured_[kMaxDevices] = {};
-    bool& configured = configured_[device_ordinal()];
-    if (!configured) {
-      DPC_CUDA(cudaFuncSetAttribute(temporal_attention_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = true;
-    }
-    temporal_attention_kernel<2><<<(unsigned)blocks, 128, smem, st>>>(qkv, rope_cos, rope_sin, pos_bias, out, total, F, HW,
-                                                                      heads, use_rope);
+    if (precise)
+      temporal_attention_mma_kernel<true, 64><<<(unsigned)blocks, 128, smem, st>>>(qkv, rope_cos, rope_sin, pos_bias, out, total, F,
+                                                                                  HW, heads, use_rope);
+    else
+      temporal_attention_mma_kernel<false, 64><<<(unsigned)blocks, 128, smem, st>>>(qkv, rope_cos, rope_sin, pos_bias, out, total, F,
+                                                                                   HW, heads, use_rope);
   }
   DPC_LAUNCH_CHECK();
   return 0;

@@ -136,9 +136,9 @@ int dpc_pack_input(const float* x, float* out, int32_t B, int32_t F, int32_t Cto
  * ------------------------------------------------------------------------------------------------------- */
 /* Temporal softmax attention over frames per pixel with RoPE on q,k and T5 relative bias — conv3d.py:293-352,
  * rotary-embedding-torch 0.8.4 rotate_queries_or_keys.  rope_cos/rope_sin: [F][32] (angle table, interleaved pairs);
- * pos_bias: [heads][F][F] or NULL; use_rope 0 skips the rotation. F <= 64.  For F <= 32 the two contractions run on
- * tensor cores (precise 0: TF32 operands, 1: 3xTF32 split products, fp32-class like the reference's einsum); for
- * 32 < F <= 64 they run as fp32 SIMT and `precise` is ignored. */
+ * pos_bias: [heads][F][F] or NULL; use_rope 0 skips the rotation. F <= 64.  The two contractions run on tensor cores
+ * (mma.sync m16n8k8; precise 0: TF32 operands, 1: 3xTF32 split products, fp32-class like the reference's einsum); frames are
+ * padded to 32 (F <= 32) or 64 (32 < F <= 64) with the padded keys masked out. */
 int dpc_temporal_attention(const float* qkv, const float* rope_cos, const float* rope_sin, const float* pos_bias,
                            float* out, int32_t B, int32_t F, int32_t HW, int32_t heads, int32_t use_rope,
                            int32_t precise, void* stream);

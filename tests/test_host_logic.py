@@ -208,3 +208,31 @@ def test_rollout_masks_match_reference(golden_dir):
 
 
 _ = so
+
+
+def test_packed_weight_cache_invalidation(golden_dir, monkeypatch):
+    """in-place edits through `.data` neither move the storage nor bump the version counter, so the packed
+    (TF32-rounded, K-major) weight copies must be dropped explicitly — or detected by the opt-in content fingerprint.
+    Versioned edits (load_state_dict, optimizer-style in-place ops on the parameter) are picked up automatically."""
+    z = np.load(os.path.join(golden_dir, "unet_small_c6.npz"))
+    cfg = uo.UnetCfg(**CASES["unet_small_c6"])
+    net = dpc.Unet3D_with_Conv3D(**CASES["unet_small_c6"])
+    net.load_state_dict(uo.make_params(cfg, int(z["seed"])), strict=True)
+    x, t = torch.from_numpy(z["x"]), torch.from_numpy(z["t"])
+    y0 = _run_unet_cpu(net, x, t, monkeypatch)
+    w = net.final_conv[1].weight
+    w.data.mul_(2.0)                                           # unversioned edit: the stale packed copy is still used ...
+    assert torch.equal(_run_unet_cpu(net, x, t, monkeypatch), y0)
+    net.invalidate_packed()                                    # ... until the caller says so
+    y1 = _run_unet_cpu(net, x, t, monkeypatch)
+    assert not torch.allclose(y1, y0)
+    net.paranoid_weight_check = True                           # or the fingerprint notices by itself
+    w.data.mul_(0.5)
+    y2 = _run_unet_cpu(net, x, t, monkeypatch)
+    assert torch.allclose(y2, y0, atol=1e-6)
+    net.paranoid_weight_check = False
+    with torch.no_grad():
+        w.mul_(2.0)                                            # versioned in-place op: picked up through p._version
+    assert torch.allclose(_run_unet_cpu(net, x, t, monkeypatch), y1, atol=1e-6)
+    net.load_state_dict(uo.make_params(cfg, int(z["seed"])), strict=True)
+    assert torch.allclose(_run_unet_cpu(net, x, t, monkeypatch), y0, atol=1e-6)
