@@ -237,6 +237,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-rollout", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
+    ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false",
+                    help="strong mode replays one captured CUDA graph per denoising step (GaussianDiffusion.use_cuda_graph, captured "
+                         "before the timed region; bit-identical to the eager loop, tests/test_sampler_gpu.py); this flag uses the "
+                         "eager per-kernel launch loop instead")
     ap.add_argument("--profile", action="store_true", help="after the timed region, print a per-launch-category CUDA-event breakdown "
                                                            "of one more step to stderr (development aid)")
     args = ap.parse_args()
@@ -301,6 +305,7 @@ def main():
         sampler.start()
     launches0 = _lib.LaunchCounter.count
     gather = None
+    g0 = 0
     if strong:
         # the public multi-GPU call: a K-step schedule through sample_sharded, global noise stream, one all-gather of the controls
         diff_k = smoke_diffusion(dpc, nets, dev, FRAMES, SIZE, timesteps=K)
@@ -309,6 +314,12 @@ def main():
             bucket = torch.empty(world * warm.shape[0], *warm.shape[1:], device=dev)
             dist.all_gather_into_tensor(bucket, warm)
             del warm, bucket
+        if args.cuda_graph:                                 # capture (warm-up + one captured step) happens outside the timed region
+            diff_k.use_cuda_graph = True
+            sample_sharded(diff_k, Bg, design_fn=design_fn, design_guidance="standard", init=init_g, global_noise=True,
+                           gather_channels=slice(3, 5))
+            launches0 = _lib.LaunchCounter.count
+        g0 = _lib.LaunchCounter.graph_launches
         torch.manual_seed(4321)                             # same generator state on every rank: global noise, sliced per rank
         ms, ctrl = time_region(lambda: sample_sharded(diff_k, Bg, design_fn=design_fn, design_guidance="standard", init=init_g,
                                                       global_noise=True, gather_channels=slice(3, 5)),
@@ -404,7 +415,9 @@ def main():
                        "sharding": ("global batch 64 sliced over ranks (sample_sharded), one all-gather of the controls per sampling run"
                                     if strong else "independent trajectories per rank, no collective"),
                        "l2": "inputs larger than L2 (activations are GBs per layer)", "precision": args.precision,
-                       "tcgen05": not args.no_tcgen05, "micro_batch": args.micro_batch or None},
+                       "tcgen05": not args.no_tcgen05, "micro_batch": args.micro_batch or None,
+                       "cuda_graph": bool(args.cuda_graph and strong),
+                       "graph_launches": (_lib.LaunchCounter.graph_launches - g0) if strong else 0},
             "clocks": sampler.summary(), "gpu_launches": launches, "e2e": e2e, "roofline": roof, "cpu_baseline": cpu,
             "rollout": rollout, "gather": gather, "weak": weak,
         }

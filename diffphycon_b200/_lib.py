@@ -81,7 +81,7 @@ _SIGNATURES = {
     "dpc_ddim_guided_step": ([c_fp] * 6 + [C.c_int32, C.POINTER(StepCoefs), c_fp, c_fp] + [C.c_int32] * 4 + [c_fp],
                              C.c_int),
     "dpc_sampler_prepare": ([c_fp] * 3 + [C.c_int32, c_fp, C.c_int32, c_fp, c_fp], C.c_int),
-    "dpc_guided_step_dev": ([C.c_int32] + [c_fp] * 10 + [C.c_int32] * 4 + [c_fp], C.c_int),
+    "dpc_guided_step_dev": ([C.c_int32] + [c_fp] * 9 + [C.c_int32] * 4 + [c_fp], C.c_int),
     "dpc_predict_x_start": ([c_fp, c_fp, C.c_float, C.c_float, C.c_int32, c_fp, C.c_int64, c_fp], C.c_int),
     "dpc_burgers_model_output": ([c_fp] * 5 + [C.c_int32] + [C.c_float] * 4 + [C.c_int32, C.c_int64, C.c_int64, c_fp], C.c_int),
     "dpc_ddpm_posterior_step": ([c_fp] * 7 + [C.c_float] * 3 + [C.c_int32] + [C.c_float] * 3 + [C.c_int64, c_fp], C.c_int),

@@ -360,7 +360,9 @@ class GaussianDiffusion(nn.Module):
         g = self._graphs.get(key)
         if g is None:
             self._graphs.clear()       # one captured schedule at a time: a graph pins its activation buffers
+            rng = torch.cuda.get_rng_state(dev)     # warm-up and capture draw noise: leave the caller's RNG stream untouched
             g = _GraphedStep(self, shape, dev, ddim, two, ts, raw, csize, cs[0])
+            torch.cuda.set_rng_state(rng, dev)
             self._graphs[key] = g
         return g.run(x, init, n)
 
