@@ -43,11 +43,12 @@ constexpr uint32_t OFF_BAR = OFF_EXCH + 2048;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 128 + 1024;     // + alignment slack
 
 struct Params {
-  const float* rope_cos;   // [32][32]
+  const float* rope_cos;   // [F][32]
   const float* rope_sin;
-  const float* pos_bias;   // [4][32][32], function of (j - i) only
+  const float* pos_bias;   // [4][F][F], function of (j - i) only
   float eps;
   int B, HW;
+  int F;                   // frames <= 32: a pixel's rows F..31 of the tile are TMA zero fill, masked as keys, clipped by the store
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -85,13 +86,13 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   // tables: RoPE angle per (frame, pair) and the relative-position bias per (head, j - i + 31)
   for (int i = threadIdx.x; i < 32 * 16; i += THREADS) {
     const int f = i >> 4, pr = i & 15;
-    rope_s[f * 20 + pr] = __ldg(p.rope_cos + f * 32 + 2 * pr);
-    rope_s[640 + f * 20 + pr] = __ldg(p.rope_sin + f * 32 + 2 * pr);
+    rope_s[f * 20 + pr] = f < p.F ? __ldg(p.rope_cos + f * 32 + 2 * pr) : 1.f;
+    rope_s[640 + f * 20 + pr] = f < p.F ? __ldg(p.rope_sin + f * 32 + 2 * pr) : 0.f;
   }
   for (int i = threadIdx.x; i < 4 * 64; i += THREADS) {
     const int h = i >> 6, d = (i & 63) - 31;
     float v = 0.f;
-    if (d <= 31) v = (d >= 0) ? __ldg(p.pos_bias + (h * 32 + 0) * 32 + d) : __ldg(p.pos_bias + (h * 32 - d) * 32 + 0);
+    if (d < p.F && -d < p.F) v = (d >= 0) ? __ldg(p.pos_bias + (h * p.F + 0) * p.F + d) : __ldg(p.pos_bias + (h * p.F - d) * p.F + 0);
     bias_s[i] = v;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -288,7 +289,9 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
               for (int e = 0; e < 2; ++e) {
-                const float v = sc[mt][nt][2 * e2 + e] + bias_h[8 * nt + 2 * t + e - row];
+                const int key = 8 * nt + 2 * t + e;
+                float v = sc[mt][nt][2 * e2 + e] + bias_h[key - row];
+                if (key >= p.F) v = -INFINITY;              // zero-filled frames beyond F are not keys
                 sc[mt][nt][2 * e2 + e] = v;
                 mx = fmaxf(mx, v);
               }
@@ -382,11 +385,12 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 }
 
-static int make_tok_map(CUtensorMap* m, const float* x, int B, int HW) {
+static int make_tok_map(CUtensorMap* m, const float* x, int B, int HW, int F) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_err(-1, "cuTensorMapEncodeTiled unavailable", __FILE__, __LINE__);
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)HW, (cuuint64_t)FR, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)HW * C * 4, (cuuint64_t)FR * HW * C * 4};
+  // the box always spans 32 frames: frames >= F are out of bounds = zero fill on load, clipped on store
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)HW, (cuuint64_t)F, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 4, (cuuint64_t)HW * C * 4, (cuuint64_t)F * HW * C * 4};
   cuuint32_t box[4] = {32, 1, (cuuint32_t)FR, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)x, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -416,12 +420,12 @@ extern "C" int dpc_temporal_block_fused(const float* x, const float* w_qkv, cons
                                         int32_t HW, int32_t C, int32_t heads, float eps, void* stream) {
   using namespace dpc;
   using namespace dpc::tb;
-  if (F != FR || C != tb::C || heads != HEADS || HW % 4 != 0) return -2;   // served by the unfused kernels
+  if (F < 1 || F > FR || C != tb::C || heads != HEADS || HW % 4 != 0) return -2;   // served by the unfused kernels
   DPC_CHECK_ARG(x && w_qkv && w_out && rope_cos && rope_sin && pos_bias && y && B > 0 && HW > 0);
   CUtensorMap mx, my, mq, mo;
-  int rc = make_tok_map(&mx, x, B, HW);
+  int rc = make_tok_map(&mx, x, B, HW, F);
   if (rc) return rc;
-  rc = make_tok_map(&my, y, B, HW);
+  rc = make_tok_map(&my, y, B, HW, F);
   if (rc) return rc;
   rc = make_w_map(&mq, w_qkv, tb::C, NQKV, 192);
   if (rc) return rc;
@@ -435,7 +439,7 @@ extern "C" int dpc_temporal_block_fused(const float* x, const float* w_qkv, cons
     configured = true;
   }
   const int num_sms = sm_count(dev);
-  Params p{rope_cos, rope_sin, pos_bias, eps, B, HW};
+  Params p{rope_cos, rope_sin, pos_bias, eps, B, HW, F};
   const int ntiles = B * (HW / 4);
   const unsigned grid = (unsigned)(ntiles < num_sms ? ntiles : num_sms);
   temporal_block_kernel<<<grid, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(mx, my, mq, mo, p);

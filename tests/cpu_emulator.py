@@ -159,7 +159,7 @@ def temporal_attention(qkv, rope_cos, rope_sin, pos_bias, out, B, F, HW, heads, 
 
 
 def temporal_block_fused(x, w_qkv, w_out, rope_cos, rope_sin, pos_bias, y, B, F, HW, Cn, heads, eps=1e-5):
-    if F != 32 or Cn != 64 or heads != 4 or HW % 4:
+    if F < 1 or F > 32 or Cn != 64 or heads != 4 or HW % 4:
         return False
     rows = B * F * HW
     v = x[: rows * Cn].reshape(rows, Cn)

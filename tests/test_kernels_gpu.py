@@ -579,13 +579,15 @@ def test_jellyfish_step_kernels_match_torch_restatement(ddim, guided):
         assert (a - b).abs().max().item() <= 1e-6
 
 
+@pytest.mark.parametrize("Fr", [32, 20, 5])
 @pytest.mark.parametrize("B,HW", [(1, 4), (2, 64), (3, 148 * 4 + 8)])
-def test_temporal_block_fused_tcgen05(B, HW):
+def test_temporal_block_fused_tcgen05(B, HW, Fr):
     """dpc_temporal_block_fused (LayerNorm + to_qkv + RoPE/bias attention + to_out + residual, one launch) against the fp32
     restatement of conv3d.py:165-174, :293-352 (tests/cpu_emulator.py).  The two projections are TF32 contractions:
-    tolerance 3e-3 of the output scale; the attention itself is fp32."""
+    tolerance 3e-3 of the output scale; the attention itself is fp32.  Fr < 32 (e.g. the jellyfish configuration's 20 frames): the
+    tile still spans 32 frame rows per pixel, the missing ones are TMA zero fill, masked as keys and clipped by the store."""
     torch.manual_seed(5)
-    Fr, Cn, heads = 32, 64, 4
+    Cn, heads = 64, 4
     x = torch.randn(B * Fr * HW * Cn) * 1.5 + 0.3
     gamma = 1 + 0.1 * torch.randn(Cn)
     wq = packing.tf32_round((torch.randn(384, Cn) / 8) * gamma[None, :]).contiguous()
@@ -643,8 +645,9 @@ def test_spatial_linear_block_fused_declines_other_shapes():
 
 def test_temporal_block_fused_declines_other_shapes():
     z = torch.zeros(16, device="cuda")
-    assert _lib.temporal_block_fused(z, z, z, z, z, z, z, 1, 16, 4, 64, 4) is False
+    assert _lib.temporal_block_fused(z, z, z, z, z, z, z, 1, 40, 4, 64, 4) is False
     assert _lib.temporal_block_fused(z, z, z, z, z, z, z, 1, 32, 4, 128, 4) is False
+    assert _lib.temporal_block_fused(z, z, z, z, z, z, z, 1, 32, 6, 64, 4) is False
 
 
 TC_2D_CASES = [
