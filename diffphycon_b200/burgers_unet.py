@@ -166,8 +166,11 @@ class Unet2D(nn.Module):
         self.invalidate_packed()
         return super()._apply(fn, *a, **k)
 
+    def _param_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
     def _ensure_packed(self, dev):
-        key = (str(dev), self.precision, tuple((p.data_ptr(), p._version) for p in self.parameters()))
+        key = (str(dev), self.precision, self._param_key())
         if self._packed is not None and self._packed_key == key:
             return self._packed
         rnd = self.precision == "tf32"

@@ -164,6 +164,12 @@ class GaussianDiffusion(nn.Module):
         self.condition_idx = condition_idx
         self.progress = False
         self._host_sched = None
+        # Step orchestration: with use_cuda_graph the network forwards of a denoising step (both U-Nets of the two-model
+        # sampler, ~270 launches at 16 KB per trajectory = launch-bound) are captured ONCE in a CUDA graph that reads the state
+        # and the batched time tensor from fixed buffers, and replayed every step; the guidance callable (user autograd) and the
+        # two fused sampler kernels stay eager.  Same kernels, same arithmetic as the eager loop (tests/test_burgers_sampler.py).
+        self.use_cuda_graph = False
+        self._net_graph = None
 
     def _sched(self):
         if self._host_sched is None:
@@ -191,18 +197,39 @@ class GaussianDiffusion(nn.Module):
         ti = int(t[0].item()) if torch.is_tensor(t) else int(t)
         return self._predict(x.contiguous(), ti, clip_x_start, **kwargs)[:2]
 
-    def _model_output(self, x, ti, **kwargs):
-        b = x.shape[0]
-        tt = torch.full((b,), ti, device=x.device, dtype=torch.long)
-        s = self._sched()
-        sr, srm1 = float(s['sqrt_recip_alphas_cumprod'][ti]), float(s['sqrt_recipm1_alphas_cumprod'][ti])
-        plane = x.shape[-1] * x.shape[-2]
-        out, xs0 = torch.empty_like(x), torch.empty_like(x)
+    def _networks(self, x, tt):
+        """The network forwards of one step (burgers.py:398-417) -> (eps, eps_w or None); mutates x for is_model_w like the reference."""
         if self.eval_two_models:
             eps_uw = self.model_uw(x, tt)
             x_w = x.clone()
             x_w[..., 0, 1:self.condition_idx, :] = 0          # burgers.py:400-401
-            eps_w = self.model_w(x_w, tt)
+            return eps_uw, self.model_w(x_w, tt)
+        if self.is_model_w:
+            x[..., 0, 1:self.condition_idx, :] = 0             # in place, like burgers.py:412
+        return self.model(x, tt), None
+
+    def _graphed_networks(self, x, ti):
+        models = (self.model_uw, self.model_w) if self.eval_two_models else (self.model,)
+        key = (tuple(x.shape), str(x.device), self.eval_two_models, self.is_model_w, self.condition_idx,
+               tuple(m._param_key() for m in models), tuple(m.precision for m in models))
+        g = self._net_graph
+        if g is None or g.key != key:
+            self._net_graph = None                             # a graph pins its activation buffers: drop the old one first
+            g = self._net_graph = _GraphedNetworks(self, x, key)
+        return g.run(x, ti)
+
+    def _model_output(self, x, ti, **kwargs):
+        b = x.shape[0]
+        s = self._sched()
+        sr, srm1 = float(s['sqrt_recip_alphas_cumprod'][ti]), float(s['sqrt_recipm1_alphas_cumprod'][ti])
+        plane = x.shape[-1] * x.shape[-2]
+        out, xs0 = torch.empty_like(x), torch.empty_like(x)
+        if self.use_cuda_graph and x.is_cuda and not x.requires_grad:
+            eps_a, eps_b = self._graphed_networks(x, ti)
+        else:
+            eps_a, eps_b = self._networks(x, torch.full((b,), ti, device=x.device, dtype=torch.long))
+        if self.eval_two_models:
+            eps_uw, eps_w = eps_a, eps_b
             ws = kwargs.get('w_scheduler')
             eta = ws(ti) if ws is not None else 1
             if self.normalize_beta:
@@ -212,11 +239,9 @@ class GaussianDiffusion(nn.Module):
                 _lib.burgers_model_output(x, eps_uw, eps_w, out, xs0, 0, self._f32((1 - self.prior_beta) * eta), 1.0, sr, srm1,
                                           self.channels, plane)
         elif self.is_model_w:
-            x[..., 0, 1:self.condition_idx, :] = 0             # in place, like burgers.py:412
-            eps = self.model(x, tt)
-            _lib.burgers_model_output(x, eps, None, out, xs0, 2, 0.0, self._f32(self.prior_beta), sr, srm1, self.channels, plane)
+            _lib.burgers_model_output(x, eps_a, None, out, xs0, 2, 0.0, self._f32(self.prior_beta), sr, srm1, self.channels, plane)
         else:
-            out = self.model(x, tt)
+            out = eps_a
             xs0 = None
         return out, xs0, sr, srm1
 
@@ -323,3 +348,37 @@ class GaussianDiffusion(nn.Module):
         sample_size = (batch_size, self.channels, *self.traj_size)
         sample_fn = self.p_sample_loop if not self.is_ddim_sampling else self.ddim_sample
         return sample_fn(sample_size, clip_denoised=clip_denoised, **kwargs)
+
+
+class _GraphedNetworks:
+    """The network forwards of one Burgers denoising step captured in a CUDA graph over fixed state / time buffers."""
+
+    def __init__(self, diff, x, key):
+        self.key, self.diff = key, diff
+        dev = x.device
+        self.x = x.detach().clone()
+        self.tt = torch.zeros(x.shape[0], dtype=torch.long, device=dev)
+        self.stream = torch.cuda.Stream(device=dev)
+        cur = torch.cuda.current_stream(dev)
+        self.stream.wait_stream(cur)
+        with torch.no_grad(), torch.cuda.stream(self.stream):   # warm-up on the capture stream: packs weights, fills the buffer pools
+            for _ in range(2):
+                diff._networks(self.x, self.tt)
+        cur.wait_stream(self.stream)
+        torch.cuda.synchronize(dev)
+        self.x.copy_(x.detach())
+        self.graph = torch.cuda.CUDAGraph()
+        c0 = _lib.LaunchCounter.count
+        with torch.no_grad(), torch.cuda.graph(self.graph, stream=self.stream):
+            self.out = diff._networks(self.x, self.tt)
+        self.kernels_per_replay = _lib.LaunchCounter.count - c0
+
+    def run(self, x, ti):
+        self.x.copy_(x)
+        self.tt.fill_(ti)
+        self.graph.replay()
+        _lib.LaunchCounter.graph_launches += 1
+        _lib.LaunchCounter.count += self.kernels_per_replay
+        if self.diff.is_model_w and not self.diff.eval_two_models:
+            x.copy_(self.x)                                     # the reference zeroes the conditioning rows of x in place
+        return self.out

@@ -139,3 +139,26 @@ def test_burgers_sampler_steps_gpu(precision, tol, golden_dir):
 @pytest.mark.parametrize("variant", list(VARIANTS))
 def test_burgers_sampler_loop_gpu(variant, golden_dir):
     check_loop(np.load(os.path.join(golden_dir, variant + ".npz")), "cuda", variant)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", list(VARIANTS))
+def test_burgers_cuda_graph_networks_equal_eager(variant, golden_dir):
+    """use_cuda_graph replays the captured network forwards (fixed state / time buffers) instead of launching ~270 kernels per
+    step: same kernels and arithmetic, so the sampled trajectories are bit-identical to the eager loop, and one graph launch per
+    network evaluation is counted."""
+    from diffphycon_b200 import _lib
+    z = np.load(os.path.join(golden_dir, variant + ".npz"))
+    nz = len([k for k in z.files if k.startswith("z")])
+    out = []
+    for graph in (False, True):
+        d, kw = make(z, "cuda", precision="tf32", variant=variant)
+        d.use_cuda_graph = graph
+        noises = [torch.from_numpy(z[f"x{T - 1}"]).cuda()] + [torch.from_numpy(z[f"z{i}"]).cuda() for i in range(nz)]
+        it = iter(noises)
+        d.sample_noise = lambda shape, dev: next(it).clone()
+        n0 = _lib.LaunchCounter.graph_launches
+        out.append(d.sample(batch_size=2, clip_denoised=True, guidance_u0=VARIANTS[variant][1], **kw))
+        if graph:
+            assert _lib.LaunchCounter.graph_launches - n0 == T
+    assert torch.equal(out[0], out[1]), (out[0] - out[1]).abs().max().item()
