@@ -587,7 +587,7 @@ def run_other_config(args, dpc, _lib, dist, dev, rank, world, local_rank, barrie
         uw.precision = w_.precision = args.precision
         diff = db.GaussianDiffusion((uw, w_), seq_length=(16, 128), timesteps=T, auto_normalize=False, use_conv2d=True, temporal=True,
                                     is_condition_u0=True, is_condition_uT=True, eval_two_models=True, prior_beta=1.5).to(dev)
-        diff.use_cuda_graph = not args.no_cuda_graph     # network forwards of a step replayed from one captured graph
+        diff.use_cuda_graph = bool(args.cuda_graph)     # network forwards of a step replayed from one captured graph
         xs = torch.linspace(0, 1, 130, device=dev)[1:-1]
         u0 = torch.exp(-((xs[None] - torch.rand(B, 1, device=dev)) ** 2) * 50) - 0.5 * torch.exp(-((xs[None] - torch.rand(B, 1, device=dev)) ** 2) * 80)
         f0 = torch.zeros(B, 10, 128, device=dev)

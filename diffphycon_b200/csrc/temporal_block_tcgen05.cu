@@ -10,10 +10,10 @@
 //           y accumulator columns of TMEM, so the out-projection MMAs (always accumulating) add the residual for free
 //   MMA   : qkv[128 x 384] = xhat[128 x 64] . Wqkv^T   (kind::tf32, N = 256 + 128, accumulators in TMEM columns 0..383)
 //   heads : one warp per (pixel, head): tcgen05.ld.16x256b hands q,k,v to the warp in the m16n8 accumulator-fragment layout;
-//           RoPE(q*scale, k) in registers, v -> the warp's 4 KB smem tile; S = q K^T (mma.sync m16n8k8 TF32, the d index
-//           permuted so that the TMEM fragments ARE the operands) + bias, base-2 softmax in registers, O = P V with the S
-//           fragments as the A operand; O overwrites the warp's (dead) V tile in the UMMA 128B-swizzle layout: the four
-//           tiles of a head are contiguous = the [128 x 32] A operand of that head's out-projection
+//           RoPE(q, k) in registers (rotated q goes back to TMEM in place), v -> the warp's 4 KB smem tile; S = q K^T
+//           (mma.sync m16n8k8 TF32, the d index permuted so that the TMEM fragments ARE the operands), scale + bias, base-2
+//           softmax in registers, O = P V with the S fragments as the A operand; the normalised O goes to TMEM where the
+//           consumed q rows were = the [128 x 32] A operand (from TMEM) of that head's out-projection
 //   MMA   : y[128 x 64] += O_h[128 x 32] . Wout[:, h*32:(h+1)*32]^T   (TMEM columns 384..447 / 448..511, alternating per tile)
 //   store : y -> swizzled smem -> TMA store
 // Warp roles (544 threads): warp 0 = control (TMEM allocation; lane 0 issues every TMA load and every tcgen05.mma);
@@ -41,7 +41,9 @@ constexpr uint32_t OFF_XA = 131072;                       // 2 buffers x 2 chunk
 constexpr uint32_t XA_BYTES = 32768;
 constexpr uint32_t OFF_VX = OFF_XA + 2 * XA_BYTES;        // V / O tiles of heads 2,3 (2 x [128 rows x 128 B]), then their store staging
 constexpr uint32_t OFF_BIAS = OFF_VX + 32768;             // [4][64]: log2(e) * bias of relative offset (j - i + 31)
-constexpr uint32_t OFF_BAR = OFF_BIAS + 1024;
+constexpr uint32_t OFF_ROPEA = OFF_BIAS + 1024;           // [8 rows g][16 pairs] (cos, sin) of frame g, pair slot XOR-swizzled by 4*(g&3)
+constexpr uint32_t OFF_ROPEB = OFF_ROPEA + 1024;          // [4][16 pairs] (cos, sin) of frame 8i: frame g + 8i by angle addition
+constexpr uint32_t OFF_BAR = OFF_ROPEB + 512;
 constexpr uint32_t SMEM_BYTES = OFF_BAR + 128;
 
 struct Params {
@@ -51,6 +53,7 @@ struct Params {
   float eps;
   int B, HW;
   int F;                   // frames <= 32: a pixel's rows F..31 of the tile are TMA zero fill, masked as keys, clipped by the store
+  int dbg;                 // development: bit 0 skip the head phase, bit 1 skip S/softmax/PV only, bit 2 skip the stores (DPC_TB_DBG)
 };
 
 // cvt.rna.tf32.f32 for finite inputs in one integer add (ptxas expands the cvt into a compare and a predicated add)
@@ -66,6 +69,14 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+__device__ __forceinline__ void tmem_st_16x256b_x4(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+
 template <bool FULL>
 __global__ void __launch_bounds__(THREADS, 1)
 temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
@@ -74,6 +85,8 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   const uint32_t base = smem_u32(smem_raw);
   uint8_t* gbase = smem_raw;
   float* bias_s = reinterpret_cast<float*>(gbase + OFF_BIAS);
+  float2* ropeA_s = reinterpret_cast<float2*>(gbase + OFF_ROPEA);
+  float2* ropeB_s = reinterpret_cast<float2*>(gbase + OFF_ROPEB);
   const uint32_t bars = base + OFF_BAR;
   const uint32_t w_full = bars, x_full = bars + 8, a_ready = bars + 24, qkv_full = bars + 32, o_ready = bars + 40;
   const uint32_t y_full = bars + 72, tmem_slot = bars + 80;
@@ -107,6 +120,16 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     float v = 0.f;
     if (d < p.F && -d < p.F) v = (d >= 0) ? __ldg(p.pos_bias + (h * p.F + 0) * p.F + d) : __ldg(p.pos_bias + (h * p.F - d) * p.F + 0);
     bias_s[i] = v * LOG2E;
+  }
+  // RoPE angle of frame g + 8i = angle(g) + angle(8i): two small tables instead of the [32][16] one (the shared memory is full);
+  // frames >= F are clamped into the table (their rows are masked as keys and never stored)
+  for (int i = threadIdx.x; i < 8 * 16 + 4 * 16; i += THREADS) {
+    const bool isA = i < 128;
+    const int row = isA ? (i >> 4) : 8 * ((i - 128) >> 4), pr = i & 15;
+    const int rc = min(row, p.F - 1) * 32 + 2 * pr;
+    const float2 v = make_float2(__ldg(p.rope_cos + rc), __ldg(p.rope_sin + rc));
+    if (isA) ropeA_s[row * 16 + (pr ^ (4 * (row & 3)))] = v;
+    else ropeB_s[(i - 128)] = v;
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -156,16 +179,15 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         umma_commit(qkv_full);
         const uint32_t ycol = tmem_base + 384 + 64 * buf;
         for (int h = 0; h < HEADS; ++h) {
-          // O_h: heads 0,1 in the (consumed) x buffer of this tile, heads 2,3 in the extra V area
-          const uint64_t o_desc = umma_desc(h < 2 ? base + OFF_XA + buf * XA_BYTES + h * 16384 : base + OFF_VX + (h - 2) * 16384);
+          // O_h sits in TMEM where q_h was (lane = token, columns 32h..32h+31): the A operand comes straight from TMEM
           mbar_wait(o_ready + 8 * h, it & 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_tf32(ycol, o_desc + (uint64_t)(2 * k), wo_desc + (uint64_t)(h * (8192 >> 4) + 2 * k), idesc64, 1u);
+            umma_tf32_ts(ycol, tmem_base + (uint32_t)(h * DH + 8 * k), wo_desc + (uint64_t)(h * (8192 >> 4) + 2 * k), idesc64, 1u);
         }
         umma_commit(y_full);
-        // this tile's x buffer (xhat, then V / O of heads 0,1) is free once the out-projection has read it
+        // this tile's x buffer (xhat, then V of heads 0,1) is free once every head has arrived (y_full also covers that)
         const int nxt = tile + 2 * (int)gridDim.x;
         if (nxt < ntiles) {
           mbar_wait(y_full, it & 1);
@@ -183,10 +205,8 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     const uint32_t fvg = (uint32_t)(2 * ((g >> 1) & 3));
     const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
     const float* bias_h = bias_s + h * 64 + 31;
-    // RoPE rows of this thread: 16*hf + g + 8*rr, clamped into the table for F < 32 (those rows are never stored)
-    int rrow[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) rrow[i] = min(g + 8 * i, p.F - 1) * 32 + 2 * t;
+    const uint32_t ropeA = base + OFF_ROPEA + (uint32_t)(g * 128 + t * 8), ropeB = base + OFF_ROPEB + (uint32_t)(t * 8);
+    const uint32_t asw = (uint32_t)(g & 3);
     int it = 0;
     bool store_pending = false;
     int prev_tile = 0;
@@ -205,7 +225,7 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       fence_async_proxy();
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) {
+      if (lane == 0 && !(p.dbg & 4)) {
         const int b = tile / tiles_b, pix = (tile - b * tiles_b) * 4 + q;
         tma_store_4d(&tmY, mine, (h - 2) * 32, pix, 0, b);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -273,55 +293,82 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       }
 
       // ================================ one (pixel, head) per warp ================================
+      if (p.dbg & 1) {
+        fence_async_proxy();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(o_ready + 8 * h);
+        continue;
+      }
       const uint32_t tq = tlane + (uint32_t)(h * DH);
       uint32_t kb[4][4][2];                              // B fragments of the rotated key: [key block nt][d block kk]
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
-        uint32_t kf[16], vf[16];                         // C-fragment layout: [4*block + {0,1: row g; 2,3: row g+8}]
-        tmem_ld_16x256b_x4(tq + 128 + ((uint32_t)(hf * 16) << 16), kf);
-        tmem_ld_16x256b_x4(tq + 256 + ((uint32_t)(hf * 16) << 16), vf);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const uint32_t lh = (uint32_t)(hf * 16) << 16;
+        {
+          uint32_t kf[16], qf[16];                       // C-fragment layout: [4*block + {0,1: row g; 2,3: row g+8}]
+          tmem_ld_16x256b_x4(tq + 128 + lh, kf);
+          tmem_ld_16x256b_x4(tq + lh, qf);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const uint32_t vchunk = (uint32_t)(((2 * b + (t >> 1)) ^ fvg) << 4) + (uint32_t)((t & 1) * 8);
+          for (int b = 0; b < 4; ++b) {
+            const float2 ra = lds64(ropeA + (((uint32_t)b ^ asw) << 5));          // frame g, pair 4b + t
 #pragma unroll
-          for (int rr = 0; rr < 2; ++rr) {               // rows 16*hf + g and + 8; RoPE pair index 4*b + t
-            const int row = 16 * hf + g + 8 * rr;
-            const float cs = __ldg(p.rope_cos + rrow[2 * hf + rr] + 8 * b), sn = __ldg(p.rope_sin + rrow[2 * hf + rr] + 8 * b);
-            const float k0 = __uint_as_float(kf[4 * b + 2 * rr]), k1 = __uint_as_float(kf[4 * b + 2 * rr + 1]);
-            // t*cos + rotate_half(t)*sin, rotate_half: (x0, x1) -> (-x1, x0)   (rotary-embedding-torch 0.8.4)
-            // MMA k positions (t, t+4) of d block b carry d = 8b+2t, 8b+2t+1.  Key (B operand, n = key 8nt+g with
-            // nt = 2hf+rr): the accumulator-fragment layout of the TMEM load IS the B-fragment layout.
-            kb[2 * hf + rr][b][0] = rtf32(fmaf(-k1, sn, k0 * cs));
-            kb[2 * hf + rr][b][1] = rtf32(fmaf(k0, sn, k1 * cs));
-            sts64(mine + row * 128 + vchunk, __uint_as_float(rtf32(__uint_as_float(vf[4 * b + 2 * rr]))),
-                  __uint_as_float(rtf32(__uint_as_float(vf[4 * b + 2 * rr + 1]))));
+            for (int rr = 0; rr < 2; ++rr) {             // rows 16*hf + g and + 8; RoPE pair index 4*b + t
+              const float2 rb = lds64(ropeB + (uint32_t)((2 * hf + rr) * 128 + b * 32));   // frame 8*(2hf+rr)
+              const float cs = fmaf(-ra.y, rb.y, ra.x * rb.x), sn = fmaf(ra.x, rb.y, ra.y * rb.x);
+              const float k0 = __uint_as_float(kf[4 * b + 2 * rr]), k1 = __uint_as_float(kf[4 * b + 2 * rr + 1]);
+              const float q0 = __uint_as_float(qf[4 * b + 2 * rr]), q1 = __uint_as_float(qf[4 * b + 2 * rr + 1]);
+              // t*cos + rotate_half(t)*sin, rotate_half: (x0, x1) -> (-x1, x0)   (rotary-embedding-torch 0.8.4)
+              // MMA k positions (t, t+4) of d block b carry d = 8b+2t, 8b+2t+1.  Key (B operand, n = key 8nt+g with
+              // nt = 2hf+rr): the accumulator-fragment layout of the TMEM load IS the B-fragment layout.
+              kb[2 * hf + rr][b][0] = rtf32(fmaf(-k1, sn, k0 * cs));
+              kb[2 * hf + rr][b][1] = rtf32(fmaf(k0, sn, k1 * cs));
+              qf[4 * b + 2 * rr] = rtf32(fmaf(-q1, sn, q0 * cs));
+              qf[4 * b + 2 * rr + 1] = rtf32(fmaf(q0, sn, q1 * cs));
+            }
+          }
+          tmem_st_16x256b_x4(tq + lh, qf);               // rotated query back in place: part 2 reloads it as the A fragments
+        }
+        {
+          uint32_t vf[16];
+          tmem_ld_16x256b_x4(tq + 256 + lh, vf);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const uint32_t vchunk = (uint32_t)(((2 * b + (t >> 1)) ^ fvg) << 4) + (uint32_t)((t & 1) * 8);
+#pragma unroll
+            for (int rr = 0; rr < 2; ++rr)
+              sts64(mine + (16 * hf + g + 8 * rr) * 128 + vchunk, __uint_as_float(rtf32(__uint_as_float(vf[4 * b + 2 * rr]))),
+                    __uint_as_float(rtf32(__uint_as_float(vf[4 * b + 2 * rr + 1]))));
           }
         }
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       __syncwarp();                                      // V rows visible to the whole warp
-      float oc[2][4][4];
-      float inv[2][2];
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
-        // ---- rotated, scaled query rows 16mt + g, + 8 as the A operand: a0/a1 = rows g/g+8 at 2t, a2/a3 at 2t+1 ----
+        const uint32_t lm = (uint32_t)(mt * 16) << 16;
+        float oc[4][4];
+        float inv[2];
+        if (p.dbg & 2) {
+#pragma unroll
+          for (int dn = 0; dn < 4; ++dn)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) oc[dn][e] = __uint_as_float(kb[dn][e][mt]);
+          inv[0] = inv[1] = 1.f;
+        } else {
+        // ---- rotated query rows 16mt + g, + 8 as the A operand: a0/a1 = rows g/g+8 at 2t, a2/a3 at 2t+1 ----
         uint32_t qa[4][4];
         {
           uint32_t qf[16];
-          tmem_ld_16x256b_x4(tq + ((uint32_t)(mt * 16) << 16), qf);
+          tmem_ld_16x256b_x4(tq + lm, qf);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-          for (int b = 0; b < 4; ++b)
-#pragma unroll
-            for (int rr = 0; rr < 2; ++rr) {
-              const float cs = __ldg(p.rope_cos + rrow[2 * mt + rr] + 8 * b) * (ATT_SCALE * LOG2E);
-              const float sn = __ldg(p.rope_sin + rrow[2 * mt + rr] + 8 * b) * (ATT_SCALE * LOG2E);
-              const float q0 = __uint_as_float(qf[4 * b + 2 * rr]), q1 = __uint_as_float(qf[4 * b + 2 * rr + 1]);
-              qa[b][rr] = rtf32(fmaf(-q1, sn, q0 * cs));
-              qa[b][2 + rr] = rtf32(fmaf(q0, sn, q1 * cs));
-            }
+          for (int b = 0; b < 4; ++b) {
+            qa[b][0] = qf[4 * b]; qa[b][1] = qf[4 * b + 2]; qa[b][2] = qf[4 * b + 1]; qa[b][3] = qf[4 * b + 3];
+          }
         }
-        // ---- S = q K^T (m16n8k8 TF32), in units of log2(e) ----
+        // ---- S = q K^T (m16n8k8 TF32) ----
         float sc[4][4];
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
@@ -331,7 +378,8 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
           for (int nt = 0; nt < 4; ++nt) mma_tf32(sc[nt], qa[kk], kb[nt][kk][0], kb[nt][kk][1]);
-        // ---- + relative bias, softmax over the 32 keys (row = 16mt + g + 8e2, key = 8nt + 2t + e); P stays unnormalised ----
+        // ---- scale (base-2 domain) + relative bias, softmax over the 32 keys (row = 16mt + g + 8e2, key = 8nt + 2t + e);
+        //      P stays unnormalised ----
 #pragma unroll
         for (int e2 = 0; e2 < 2; ++e2) {
           const int row = 16 * mt + g + 8 * e2;
@@ -341,7 +389,7 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
               const int key = 8 * nt + 2 * t + e;
-              float v = sc[nt][2 * e2 + e] + bias_h[key - row];
+              float v = fmaf(sc[nt][2 * e2 + e], ATT_SCALE * LOG2E, bias_h[key - row]);
               if (!FULL && key >= p.F) v = -INFINITY;    // zero-filled frames beyond F are not keys
               sc[nt][2 * e2 + e] = v;
               mx = fmaxf(mx, v);
@@ -359,13 +407,13 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             }
           l += __shfl_xor_sync(0xffffffffu, l, 1);
           l += __shfl_xor_sync(0xffffffffu, l, 2);
-          inv[mt][e2] = rcp_approx(l);
+          inv[e2] = rcp_approx(l);
         }
         // ---- O = P V: the S accumulators are the A operand (k positions t, t+4 <-> keys 8kb+2t, 8kb+2t+1) ----
 #pragma unroll
         for (int dn = 0; dn < 4; ++dn)
 #pragma unroll
-          for (int e = 0; e < 4; ++e) oc[mt][dn][e] = 0.f;
+          for (int e = 0; e < 4; ++e) oc[dn][e] = 0.f;
 #pragma unroll
         for (int kj = 0; kj < 4; ++kj) {
           uint32_t pa[4];
@@ -379,20 +427,24 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           for (int dn = 0; dn < 4; ++dn) {
             const uint32_t a0 = vrow + (uint32_t)(((2 * dn + (g >> 2)) ^ fv) << 4);
             const uint32_t b0 = __float_as_uint(lds32(a0)), b1 = __float_as_uint(lds32(a0 + 128));
-            mma_tf32(oc[mt][dn], pa, b0, b1);
+            mma_tf32(oc[dn], pa, b0, b1);
           }
         }
-      }
-      __syncwarp();                                      // every lane is done reading the V rows
-      // ---- normalised O rows overwrite the V tile in the UMMA layout: A operand of this head's out-projection ----
-#pragma unroll
-      for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int dn = 0; dn < 4; ++dn) {
-          const uint32_t ob = mine + (uint32_t)((16 * mt + g) * 128) + (uint32_t)(((2 * dn + (t >> 1)) ^ g) << 4) + (uint32_t)((t & 1) * 8);
-          sts64(ob, oc[mt][dn][0] * inv[mt][0], oc[mt][dn][1] * inv[mt][0]);
-          sts64(ob + 8 * 128, oc[mt][dn][2] * inv[mt][1], oc[mt][dn][3] * inv[mt][1]);
         }
+        // ---- normalised O rows -> TMEM where the (consumed) rotated query rows were: A operand of the out-projection ----
+        {
+          uint32_t ov[16];
+#pragma unroll
+          for (int dn = 0; dn < 4; ++dn) {
+            ov[4 * dn + 0] = __float_as_uint(oc[dn][0] * inv[0]);
+            ov[4 * dn + 1] = __float_as_uint(oc[dn][1] * inv[0]);
+            ov[4 * dn + 2] = __float_as_uint(oc[dn][2] * inv[1]);
+            ov[4 * dn + 3] = __float_as_uint(oc[dn][3] * inv[1]);
+          }
+          tmem_st_16x256b_x4(tq + lm, ov);
+        }
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       fence_async_proxy();
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(o_ready + 8 * h);
@@ -462,7 +514,8 @@ extern "C" int dpc_temporal_block_fused(const float* x, const float* w_qkv, cons
     configured = true;
   }
   const int num_sms = sm_count(dev);
-  Params p{rope_cos, rope_sin, pos_bias, eps, B, HW, F};
+  static const int dbg = getenv("DPC_TB_DBG") ? atoi(getenv("DPC_TB_DBG")) : 0;
+  Params p{rope_cos, rope_sin, pos_bias, eps, B, HW, F, dbg};
   const int ntiles = B * (HW / 4);
   const unsigned grid = (unsigned)(ntiles < num_sms ? ntiles : num_sms);
   if (F == FR)
