@@ -88,8 +88,8 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
   float2* ropeA_s = reinterpret_cast<float2*>(gbase + OFF_ROPEA);
   float2* ropeB_s = reinterpret_cast<float2*>(gbase + OFF_ROPEB);
   const uint32_t bars = base + OFF_BAR;
-  const uint32_t w_full = bars, x_full = bars + 8, a_ready = bars + 24, qkv_full = bars + 32, o_ready = bars + 40;
-  const uint32_t y_full = bars + 72, tmem_slot = bars + 80;
+  const uint32_t w_full = bars, x_full = bars + 8, a_ready = bars + 24, qk_full = bars + 32, o_ready = bars + 40;
+  const uint32_t y_full = bars + 72, v_full = bars + 80, y_read = bars + 88, tmem_slot = bars + 104;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_b = p.HW / 4;
@@ -102,8 +102,10 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     }
     mbar_init(w_full, 1);
     for (int i = 0; i < 2; ++i) mbar_init(x_full + 8 * i, 1);
-    mbar_init(a_ready, 512);
-    mbar_init(qkv_full, 1);
+    mbar_init(a_ready, 256);
+    mbar_init(qk_full, 1);
+    mbar_init(v_full, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(y_read + 8 * i, 256);
     for (int i = 0; i < 4; ++i) mbar_init(o_ready + 8 * i, 128);
     mbar_init(y_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -162,21 +164,37 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       const uint64_t wq_desc = umma_desc(base + OFF_WQ), wo_desc = umma_desc(base + OFF_WO);
       mbar_wait(w_full, 0);
       int it = 0;
+      long long pc[6] = {0, 0, 0, 0, 0, 0}, pt = clock64();
+      auto lap = [&](int i) { if (p.dbg & 8) { const long long t = clock64(); pc[i] += t - pt; pt = t; } };
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int buf = it & 1;
         const uint64_t xa_desc = umma_desc(base + OFF_XA + buf * XA_BYTES);
         mbar_wait(a_ready, it & 1);
+        lap(0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // q and k first (the head warps rotate them while the v projection still runs), then v
 #pragma unroll
         for (int c = 0; c < 2; ++c)
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t a = xa_desc + (uint64_t)(c * (16384 >> 4) + 2 * k);
-            const uint64_t b = wq_desc + (uint64_t)(c * (49152 >> 4) + 2 * k);
-            umma_tf32(tmem_base + 0, a, b, idesc256, (uint32_t)(c | k));
-            umma_tf32(tmem_base + 256, a, b + (uint64_t)((256 * 128) >> 4), idesc128, (uint32_t)(c | k));
-          }
-        umma_commit(qkv_full);
+          for (int k = 0; k < 4; ++k)
+            umma_tf32(tmem_base + 0, xa_desc + (uint64_t)(c * (16384 >> 4) + 2 * k), wq_desc + (uint64_t)(c * (49152 >> 4) + 2 * k),
+                      idesc256, (uint32_t)(c | k));
+        umma_commit(qk_full);
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_tf32(tmem_base + 256, xa_desc + (uint64_t)(c * (16384 >> 4) + 2 * k),
+                      wq_desc + (uint64_t)(c * (49152 >> 4) + 2 * k + ((256 * 128) >> 4)), idesc128, (uint32_t)(c | k));
+        umma_commit(v_full);
+        lap(1);
+        // the previous tile's x buffer (xhat, then V of heads 0,1) is free once its out-projection has retired (it was issued
+        // before these MMAs): prefetch the next tile into it
+        if (it >= 1 && tile + (int)gridDim.x < ntiles) {
+          mbar_wait(y_full, (it - 1) & 1);
+          load_x(tile + gridDim.x, buf ^ 1);
+        }
+        lap(2);
         const uint32_t ycol = tmem_base + 384 + 64 * buf;
         for (int h = 0; h < HEADS; ++h) {
           // O_h sits in TMEM where q_h was (lane = token, columns 32h..32h+31): the A operand comes straight from TMEM
@@ -187,13 +205,11 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
             umma_tf32_ts(ycol, tmem_base + (uint32_t)(h * DH + 8 * k), wo_desc + (uint64_t)(h * (8192 >> 4) + 2 * k), idesc64, 1u);
         }
         umma_commit(y_full);
-        // this tile's x buffer (xhat, then V of heads 0,1) is free once every head has arrived (y_full also covers that)
-        const int nxt = tile + 2 * (int)gridDim.x;
-        if (nxt < ntiles) {
-          mbar_wait(y_full, it & 1);
-          load_x(nxt, buf);
-        }
+        lap(3);
       }
+      if ((p.dbg & 8) && blockIdx.x == 0 && it > 0)
+        printf("temporal block control: per tile clk: wait a_ready %lld, issue qkv %lld, wait y_full(prev)+load %lld, wait o_ready+issue out %lld (%d tiles)\n",
+               pc[0] / it, pc[1] / it, pc[2] / it, pc[3] / it, it);
     }
   } else {
     // ------------------------------------------- row warps ----------------------------------------------
@@ -210,6 +226,8 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
     int it = 0;
     bool store_pending = false;
     int prev_tile = 0;
+    long long pc[6] = {0, 0, 0, 0, 0, 0}, pt = clock64();
+    auto lap = [&](int i) { if (p.dbg & 8) { const long long t = clock64(); pc[i] += t - pt; pt = t; } };
 
     auto store_epilogue = [&](int tile, int itx) {       // heads 2,3: y (residual included) of tile `tile` -> global
       const uint32_t mine = base + OFF_VX + (uint32_t)(((h - 2) * 4 + q) * 4096);
@@ -218,6 +236,8 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       uint32_t yv[32];
       tmem_ld32(tlane + 384 + 64 * (itx & 1) + (h - 2) * 32, yv);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(y_read + 8 * (itx & 1));               // this y buffer may take the raw x of tile itx + 2
 #pragma unroll
       for (int j = 0; j < 8; ++j)
         sts128(mine + lane * 128 + ((j ^ sw) << 4), __uint_as_float(yv[4 * j]), __uint_as_float(yv[4 * j + 1]),
@@ -236,16 +256,22 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       const int buf = it & 1;
       const uint32_t xa = base + OFF_XA + buf * XA_BYTES;
       const uint32_t mine = h < 2 ? xa + (uint32_t)((h * 4 + q) * 4096) : base + OFF_VX + (uint32_t)(((h - 2) * 4 + q) * 4096);
+      lap(5);
       if (h < 2) {
         // ---- LayerNorm over the 64 channels of token r, in place for chunk h; raw x -> the y accumulator (residual).
         //      Moments about the row's first element (shifted single pass), chunk 0 then chunk 1 in both threads of a row.
         mbar_wait(x_full + 8 * buf, (it >> 1) & 1);
+        lap(0);
         float x[32];
         const uint32_t xrow = xa + h * 16384 + r * 128, orow = xa + (h ^ 1) * 16384 + r * 128;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 v = lds128(xrow + ((j ^ sw) << 4));
           x[j * 4 + 0] = v.x; x[j * 4 + 1] = v.y; x[j * 4 + 2] = v.z; x[j * 4 + 3] = v.w;
+        }
+        if (it >= 2) {                                     // the store epilogue of tile it - 2 has read this y buffer
+          mbar_wait(y_read + 8 * buf, ((it >> 1) - 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         {
           uint32_t u[32];
@@ -282,11 +308,15 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
           store_pending = true;
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(a_ready);
+      if (h < 2) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(a_ready);
+      }
       prev_tile = tile;
-      mbar_wait(qkv_full, it & 1);
+      lap(1);
+      mbar_wait(qk_full, it & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      lap(2);
       if (h >= 2 && store_pending) {                     // the TMA store has finished reading this warp's tile
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncwarp();
@@ -331,6 +361,10 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
         }
         {
           uint32_t vf[16];
+          if (hf == 0) {
+            mbar_wait(v_full, it & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
           tmem_ld_16x256b_x4(tq + 256 + lh, vf);
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
@@ -345,6 +379,7 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       }
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       __syncwarp();                                      // V rows visible to the whole warp
+      lap(3);
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         const uint32_t lm = (uint32_t)(mt * 16) << 16;
@@ -448,7 +483,11 @@ temporal_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_cons
       fence_async_proxy();
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(o_ready + 8 * h);
+      lap(4);
     }
+    if ((p.dbg & 8) && blockIdx.x == 0 && lane == 0 && q == 0 && it > 0)
+      printf("temporal block head %d: per tile clk: wait x_full %lld, LN or epilogue %lld, wait qk_full %lld, part 1 %lld, part 2 %lld, loop %lld\n", h,
+             pc[0] / it, pc[1] / it, pc[2] / it, pc[3] / it, pc[4] / it, pc[5] / it);
     if (h >= 2) {                                        // drain: the last tile's store
       if (it > 0) store_epilogue(prev_tile, it - 1);
       if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
