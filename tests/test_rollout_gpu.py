@@ -68,3 +68,23 @@ def test_rollout_properties_full_length():
     assert torch.equal(out["densitys"][1, 0], out["densitys"][1, -1])        # ... so its density never moves
     assert (out["zero_densitys"] <= out["densitys"] + 1e-6).all()
     assert ((out["smoke_out"] >= 0) & (out["smoke_out"] <= 1)).all()
+
+
+@pytest.mark.parametrize("cs", [2, 4, 8])
+def test_rollout_every_cluster_size_matches_golden(cs, golden_dir, monkeypatch):
+    """The launcher picks 2, 4 or 8 CTAs per trajectory from the batch size (the widest cluster that keeps all trajectories in one
+    wave).  The cluster size only changes the order in which the CTA totals of the dot products are summed: every size must
+    hold the reference golden at 1e-8, and a batch must give every trajectory the same result as a single-trajectory launch."""
+    monkeypatch.setenv("DPC_ROLLOUT_CLUSTER", str(cs))
+    z = np.load(os.path.join(golden_dir, "smoke_rollout.npz"))
+    sim = sr.init_sim_128()
+    d, zd, vs, _, _, rec = sr.solver(sim, z["init_velocity"], z["init_density"], z["c1"], z["c2"], 4)
+    assert np.abs(vs - z["velocitys"]).max() <= 1e-8 * np.abs(z["velocitys"]).max()
+    assert np.abs(d - z["densitys"]).max() <= 2e-6 and np.abs(zd - z["zero_densitys"]).max() <= 2e-6
+    # batched launch (3 copies + a different 4th trajectory): bit-identical per trajectory, whatever its neighbours are
+    c1 = torch.from_numpy(np.stack([z["c1"]] * 3 + [z["c1"][::-1].copy()])).float().cuda()
+    c2 = torch.from_numpy(np.stack([z["c2"]] * 3 + [z["c2"][::-1].copy()])).float().cuda()
+    dens = torch.from_numpy(np.stack([z["init_density"]] * 4)).float().cuda()
+    out = sr.solver_batch(sim, z["init_velocity"][None], dens, c1, c2, 4)
+    assert torch.equal(out["velocitys"][0], out["velocitys"][1]) and torch.equal(out["velocitys"][0], out["velocitys"][2])
+    assert np.abs(out["velocitys"][0].cpu().numpy() - vs).max() == 0.0
