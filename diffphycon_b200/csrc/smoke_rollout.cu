@@ -16,8 +16,8 @@
 // depends on CS only).  One stencil pass, two cluster reductions and one halo barrier per iteration.  The Laplacian is
 // applied from 4 neighbour bits + a small integer diagonal per cell (no matrix is materialised — the reference rebuilds a
 // scipy sparse matrix every step).  Round 1 ran one CTA per trajectory with x in an L2 workspace and two stencil passes
-// (three fp64 vectors do not fit one SM): 18 us per iteration; this kernel: 6.8 us (CS = 2, 64 trajectories), 5.1 us (CS = 4),
-// 4.0 us (CS = 8), of which ~2.4 us are the three cluster barriers (tools/cluster_sync_probe.cu) and the rest is bounded by the
+// (three fp64 vectors do not fit one SM): 18 us per iteration; this kernel: 6.8 us (CS = 2, 64 trajectories), 5.4 us (CS = 4,
+// 32 trajectories), of which ~2.4 us are the three cluster barriers (tools/cluster_sync_probe.cu) and the rest is bounded by the
 // shared-memory passes over fp64 vectors (two wavefronts per access) — measured with DPC_ROLLOUT_PROF=1.  The velocity / density fields of the other phases stay in
 // global workspaces (L2-resident); a cluster barrier (release / acquire) orders the phases.
 // The kernel is latency bound (127 500 strictly sequential CG iterations per trajectory), not HBM bound.
@@ -195,7 +195,8 @@ __global__ void __launch_bounds__(THREADS, 1) smoke_rollout_kernel(const Args a)
     if (p_up && l < N) p_up[(RPC + 1) * N + l] = v;                      // neighbours above always own RPC rows
     if (p_dn && l >= ncell - N) p_dn[l - (ncell - N)] = v;
   };
-  long long prof_t[7] = {0, 0, 0, 0, 0, 0, 0};
+  long long prof_t[7] = {0, 0, 0, 0, 0, 0, 0}, prof_f[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tf0 = 0;
+  auto flap = [&](int i) { if (a.prof) { const long long t = clock64(); prof_f[i] += t - tf0; tf0 = t; } };
   int slot = 0;
   auto next_slot = [&]() { const int s0 = slot; slot = (slot + 1) & (RED_SLOTS - 1); return s0; };
 
@@ -262,6 +263,7 @@ __global__ void __launch_bounds__(THREADS, 1) smoke_rollout_kernel(const Args a)
     double* vcur = vel0 + (size_t)((frame + 1) & 1) * NV * 2;
     const float* c1f = a.c1 + ((size_t)b * a.nt + frame / ti) * nx * nx;
     const float* c2f = a.c2 + ((size_t)b * a.nt + frame / ti) * nx * nx;
+    if (a.prof) tf0 = clock64();
     // ---- A. control injection + boundary mask (es.py:128-142, flow.py:294-298) ----
     for (int s = s_lo + tid; s < s_hi; s += THREADS) {
       const int y = s >> 7, x = s & 127;
@@ -276,7 +278,9 @@ __global__ void __launch_bounds__(THREADS, 1) smoke_rollout_kernel(const Args a)
       vcur[2 * s] = vx * (double)a.vmask[2 * s];
       vcur[2 * s + 1] = vy * (double)a.vmask[2 * s + 1];
     }
+    flap(0);
     cluster.sync();                                       // the divergence reads the row below (next CTA's band)
+    flap(1);
     // ---- B. divergence -> r (= p: aliased in the reference), x = 0 ----
     double rr[PER];
     double mx = 0.0;
@@ -300,6 +304,7 @@ __global__ void __launch_bounds__(THREADS, 1) smoke_rollout_kernel(const Args a)
       cluster_reduce<CS, THREADS, 1>(red, true, s_part, s_cl, next_slot(), rk);   // its barrier also orders the p writes (band + halos) before the stencil reads
       mx = red[0];
     }
+    flap(2);
     // ---- C. conjugate gradient (phi/solver/base.py:56-103) ----
     int it = 0;
     long long tk0 = 0;
@@ -357,6 +362,7 @@ __global__ void __launch_bounds__(THREADS, 1) smoke_rollout_kernel(const Args a)
       if (a.prof) { const long long t = clock64(); prof_t[5] += t - tk0; prof_t[6] += 1; }
       ++it;
     }
+    flap(3);
     // ---- D. pressure to shared memory (band + halos: the gradient reads the row above) ----
 #pragma unroll
     for (int j = 0; j < PER; ++j) {
@@ -381,6 +387,7 @@ __global__ void __launch_bounds__(THREADS, 1) smoke_rollout_kernel(const Args a)
       vout[2 * s] = nvx;
       vout[2 * s + 1] = nvy;
     }
+    flap(4);
     cluster.sync();                                       // the advection reads the row below
     // ---- F. advect density and zeroed density (nd.py:422-427, scipy_backend.py:58-77, :181-185) ----
     const float* din = dws + (size_t)(frame & 1) * 2 * NC;
@@ -418,6 +425,7 @@ __global__ void __launch_bounds__(THREADS, 1) smoke_rollout_kernel(const Args a)
         if (bk >= 0) red8[bk] += (double)zv; else red8[7] += (double)zv;
       }
     }
+    flap(5);
     // ---- G. smoke accounting (es.py:279-305) ----
     cluster_reduce<CS, THREADS, 8>(red8, false, s_part, s_cl, next_slot(), rk);
     double bsum = 0.0;
@@ -438,6 +446,7 @@ __global__ void __launch_bounds__(THREADS, 1) smoke_rollout_kernel(const Args a)
         dnew[NC + i] = zv;
       }
     }
+    flap(6);
     __syncthreads();                                      // the frame outputs below read this CTA's own band only
     // ---- H. frame outputs ----
     float* dout = a.densitys + ((size_t)b * a.T + frame + 1) * NV;
@@ -456,7 +465,11 @@ __global__ void __launch_bounds__(THREADS, 1) smoke_rollout_kernel(const Args a)
       a.iterations[(size_t)b * a.T + frame + 1] = it;
     }
     cluster.sync();                                       // next frame: the advection gathers from every band of dnew
+    flap(7);
   }
+  if (a.prof && b == 0 && tid == 0 && rk == 0)
+    printf("rollout frame phases (total clk over %d frames): A %lld, sync %lld, B div+reduce %lld, C cg %lld, D+E %lld, sync+F %lld, G %lld, H+sync %lld\n", a.T - 1,
+           prof_f[0], prof_f[1], prof_f[2], prof_f[3], prof_f[4], prof_f[5], prof_f[6], prof_f[7]);
   if (a.prof && b == 0 && tid == 0 && prof_t[6] > 0)
     printf("rollout CG rank %d of %d: per iteration clk: stencil+dots %lld, reduce1 %lld, update %lld, reduce2 %lld, p update %lld, halo sync %lld (%lld iterations)\n",
            rk, CS, prof_t[0] / prof_t[6], prof_t[1] / prof_t[6], prof_t[2] / prof_t[6], prof_t[3] / prof_t[6], prof_t[4] / prof_t[6], prof_t[5] / prof_t[6], prof_t[6]);
@@ -489,6 +502,32 @@ static int launch(const Args& a, int B, cudaStream_t st) {
   return 0;
 }
 
+// co-resident clusters of CS CTAs on this device (cached per device): a cluster must fit one GPC, so this is well below
+// num_SMs / CS for CS = 8
+template <int CS, int THREADS>
+static int max_clusters() {
+  static int cached[kMaxDevices] = {};
+  int& n = cached[device_ordinal()];
+  if (n) return n;
+  constexpr int RPC = (N + CS - 1) / CS;
+  const size_t smem = (size_t)((RPC + 2) * N + 1 + RPC * N + 1 + RED_SLOTS * 32 * RED_MAXV + RED_SLOTS * RED_MAXV * 8 + RED_SLOTS * RED_MAXV + 8) * sizeof(double);
+  if (cudaFuncSetAttribute(smoke_rollout_kernel<CS, THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return n = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(CS * 64));
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  int v = 0;
+  if (cudaOccupancyMaxActiveClusters(&v, smoke_rollout_kernel<CS, THREADS>, &cfg) != cudaSuccess || v < 1) v = 1;
+  return n = v;
+}
+
 }  // namespace rollout
 }  // namespace dpc
 
@@ -508,9 +547,12 @@ extern "C" int dpc_smoke_rollout(const int8_t* fluid_mask, const float* velocity
   a.velocitys = velocitys; a.smoke_out = smoke_out; a.iterations = iterations;
   a.nt = nt; a.nx = nx; a.T = T; a.dt = dt; a.accuracy = accuracy; a.max_iterations = max_iterations;
   { static const int prof = getenv("DPC_ROLLOUT_PROF") ? atoi(getenv("DPC_ROLLOUT_PROF")) : 0; a.prof = prof; }
-  // CTAs per trajectory: the widest cluster that still runs every trajectory in one wave (DPC_ROLLOUT_CLUSTER overrides).  The
-  // reductions sum the CTA totals in rank order, so results depend on the cluster size at the 1e-16 level only.
-  int cs = (B * 8 <= sm_count(device_ordinal())) ? 8 : (B * 4 <= sm_count(device_ordinal())) ? 4 : 2;
+  // CTAs per trajectory: 4 while every trajectory still runs in one wave (cudaOccupancyMaxActiveClusters), else 2
+  // (DPC_ROLLOUT_CLUSTER = 2 / 4 / 8 overrides; eight-CTA clusters must fit one GPC: ~8 co-resident on a B200 = two waves at 16).
+  // Measured wall time for 32 frames (tools/time_rollout.py): 16 trajectories 161 / 111 / 149 ms for 2 / 4 / 8 CTAs, 32 trajectories
+  // 121 / 86 / 182 ms, 64 trajectories 109 ms with 2: eight-CTA clusters pay more in the three barriers per iteration than they
+  // gain.  The reductions sum the CTA totals in rank order, so results depend on the cluster size at the 1e-16 level only.
+  int cs = (B <= max_clusters<4, 512>()) ? 4 : 2;
   if (const char* e = getenv("DPC_ROLLOUT_CLUSTER")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) cs = v; }
   if (cs == 8) return launch<8, 512>(a, B, (cudaStream_t)stream);
   if (cs == 4) return launch<4, 512>(a, B, (cudaStream_t)stream);
