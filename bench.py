@@ -508,7 +508,7 @@ def run_rollout(dpc, x, dev, frames=256):
     rms = e0.elapsed_time(e1)
     return {"trajectories": B, "frames": frames, "ms_total": rms, "trajectories_per_s": B / (rms / 1e3),
             "mean_cg_iterations": float(ro["iterations"][:, 1:].float().mean()),
-            "note": "one persistent CTA per trajectory, fp64 CG with the reference's 500-iteration cap; the "
+            "note": "a thread-block cluster of 2 or 4 CTAs per trajectory, fp64 CG with the reference's 500-iteration cap; the "
                     "reference needs ~48 s per trajectory on one CPU core (SURVEY.md section 6)"}
 
 

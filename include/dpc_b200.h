@@ -244,7 +244,8 @@ int dpc_predict_x_start(const float* x, const float* eps, float sqrt_recip, floa
  * Post-sampling smoke rollout — dataset/apps/evaluate_solver.py:205-310 (solver), :118-147 (get_envolve) with
  * phi/flow.py:294-327, phi/math/nd.py:332-427, :602-614, phi/math/scipy_backend.py:58-77, :181-185,
  * phi/solver/sparse.py:27-119 and phi/solver/base.py:56-103 (plain CG, max|r| >= accuracy, <= max_iterations).
- * One persistent CTA per trajectory runs all T-1 simulation steps in fp64 (the reference's NumPy precision).
+ * One launch runs all T-1 simulation steps in fp64 (the reference's NumPy precision); a thread-block cluster of 4 (while every
+ * trajectory runs in one wave) or 2 CTAs per trajectory keeps the CG vectors on chip (x_ws is unused since round 2).
  * fluid_mask [127][127] int8 (1 fluid / 0 obstacle), velocity_mask [128][128][2] fp32 (component 0 = x faces),
  * init_velocity [B][128][128][2], init_density [B][nx][nx], c1/c2 [B][nt][nx][nx] (tiled in space and time on the fly,
  * es.py:223-227).  Workspaces: vel_ws B*2*128*128*2 doubles, x_ws B*127*127 doubles, dens_ws B*4*127*127 floats.
