@@ -73,6 +73,7 @@ _SIGNATURES = {
     "dpc_spatial_attention_mma": ([c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_smoke_eval_sums": ([c_fp] * 5 + [C.c_int32] * 6 + [c_fp], C.c_int),
     "dpc_gn_fold": ([c_fp] * 5 + [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_float, c_fp], C.c_int),
+    "dpc_gn_stats_merge": ([c_fp] * 2 + [C.c_int32] * 3 + [c_fp], C.c_int),
     "dpc_spatial_linear_attention": ([c_fp, c_fp, c_fp, C.c_int32, C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_time_embed": ([c_fp] * 8 + [C.c_int32, C.c_int32, c_fp], C.c_int),
     "dpc_time_proj": ([c_fp] * 4 + [C.c_int32] * 3 + [c_fp], C.c_int),
@@ -257,6 +258,12 @@ def groupnorm_silu(y, stats, gamma, beta, scale_shift, ss_stride, ss_off, residu
 def gn_fold(stats, gamma, beta, scale, shift, B, rows_per_sample, Cn, groups, eps=1e-5):
     check(lib().dpc_gn_fold(ptr(stats), ptr(gamma), ptr(beta), ptr(scale), ptr(shift), B, rows_per_sample, Cn, groups, eps,
                             stream_ptr()), "dpc_gn_fold")
+    LaunchCounter.count += 1
+
+
+@_timed("gn_stats_merge")
+def gn_stats_merge(stats_in, stats_out, B, groups_in, groups_out):
+    check(lib().dpc_gn_stats_merge(ptr(stats_in), ptr(stats_out), B, groups_in, groups_out, stream_ptr()), "dpc_gn_stats_merge")
     LaunchCounter.count += 1
 
 

@@ -138,6 +138,7 @@ class Unet2D(nn.Module):
         self.final_conv = nn.Conv2d(dim, self.out_dim, 1)
         # engine state
         self.precision = "tf32"     # or "3xtf32" (fp32-class), see Unet3D_with_Conv3D
+        self.use_tcgen05 = True     # TF32 mode: 3x3 / 1x1 layers on the TMA + tcgen05 kernel where it tiles the shape
         self._packed = None
         self._packed_key = None
         self._taps: Dict[tuple, torch.Tensor] = {}
@@ -283,12 +284,33 @@ class Unet2D(nn.Module):
             p.taps, p.ntaps = self._tap(kh, kw, h, wd, dev).data_ptr(), kh * kw
             p.Cout, p.Npad, p.Kpad = cout, w.shape[0], w.shape[1]
             p.out_layout, p.precise = out_layout, (1 if precise else 0)
-            _lib.conv(p, tcgen05=False)
+            if not tc:
+                _lib.conv(p, tcgen05=False)
+                return
+            # TF32 mode: the TMA / tcgen05 kernel serves the 3x3 and 1x1 layers whose channel counts it tiles (multiples of 32 in, 64 /
+            # 128 / 256 / 512 out); its epilogue produces GroupNorm(8) statistics, merged here into the coarser grouping of
+            # resnet_block_groups = 1 / 2 / 4 nets.  Everything it declines (-2) runs on the mma.sync implicit GEMM as before.
+            if gn is not None and groups != 8 and 8 % groups == 0 and cout % 8 == 0:
+                s8 = stats8[slot8[0] * B * 16:(slot8[0] + 1) * B * 16]
+                slot8[0] += 1
+                p.gn_stats, p.gn_groups = s8.data_ptr(), 8
+                if _lib.conv(p, tcgen05=True, tc_only=True):
+                    _lib.gn_stats_merge(s8, gn, B, 8, groups)
+                    return
+                p.gn_stats, p.gn_groups = gn.data_ptr(), groups
+                _lib.conv(p, tcgen05=False)
+            else:
+                _lib.conv(p, tcgen05=True)
 
         n_gn = 2 * len(self._resnets())
         stats = pool.get(n_gn * B * groups * 2, torch.float64)
         stats.zero_()
         slot = [0]
+        tc = bool(self.use_tcgen05) and not precise
+        stats8, slot8 = None, [0]
+        if tc and groups != 8:
+            stats8 = pool.get(n_gn * B * 16, torch.float64)
+            stats8.zero_()
 
         def next_stats():
             s = stats[slot[0] * B * groups * 2:(slot[0] + 1) * B * groups * 2]
@@ -413,6 +435,8 @@ class Unet2D(nn.Module):
         pool.put(f0)
         pool.put(ss)
         pool.put(stats)
+        if stats8 is not None:
+            pool.put(stats8)
         return out
 
 

@@ -279,6 +279,25 @@ extern "C" int dpc_gn_fold(const double* stats, const float* gamma, const float*
   return 0;
 }
 
+__global__ void gn_stats_merge_kernel(const double* __restrict__ in, double* __restrict__ out, int B, int gin, int gout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;       // (b, g, k): k = 0 sum, 1 sum of squares
+  if (i >= B * gout * 2) return;
+  const int k = i & 1, g = (i >> 1) % gout, b = (i >> 1) / gout, r = gin / gout;
+  double s = 0.0;
+  for (int j = 0; j < r; ++j) s += in[((size_t)b * gin + g * r + j) * 2 + k];    // fixed order: deterministic
+  out[i] += s;
+}
+
+extern "C" int dpc_gn_stats_merge(const double* stats_in, double* stats_out, int32_t B, int32_t groups_in, int32_t groups_out,
+                                  void* stream) {
+  using namespace dpc;
+  DPC_CHECK_ARG(stats_in && stats_out && B > 0 && groups_in > 0 && groups_out > 0 && groups_in % groups_out == 0);
+  gn_stats_merge_kernel<<<(unsigned)((B * groups_out * 2 + 127) / 128), 128, 0, (cudaStream_t)stream>>>(stats_in, stats_out, B, groups_in,
+                                                                                                     groups_out);
+  DPC_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int dpc_layernorm_channels(const float* x, const float* gamma, const float* residual, float* out, int64_t rows,
                                       int32_t C, float eps, int32_t use_rsqrt, void* stream) {
   using namespace dpc;

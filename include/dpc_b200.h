@@ -114,6 +114,10 @@ int dpc_groupnorm_silu(const float* y, const double* stats, const float* gamma, 
  * (stats as produced by the conv epilogues: [B][groups][2] doubles = sum, sum of squares over rows_per_sample*C/groups values). */
 int dpc_gn_fold(const double* stats, const float* gamma, const float* beta, float* scale, float* shift, int32_t B,
                 int64_t rows_per_sample, int32_t C, int32_t groups, float eps, void* stream);
+/* GroupNorm statistics of a coarser grouping from a finer one: stats_out[b][g] += sum of the groups_in / groups_out consecutive
+ * entries of stats_in (sum and sum of squares are additive over channels).  The tcgen05 conv epilogue produces GroupNorm(8)
+ * statistics; the Burgers U-Nets use GroupNorm(1) blocks (model/burgers_1d/unet.py:95-111 with resnet_block_groups = 1). */
+int dpc_gn_stats_merge(const double* stats_in, double* stats_out, int32_t B, int32_t groups_in, int32_t groups_out, void* stream);
 int dpc_layernorm_channels(const float* x, const float* gamma, const float* residual, float* out, int64_t rows,
                            int32_t C, float eps, int32_t use_rsqrt, void* stream);
 
