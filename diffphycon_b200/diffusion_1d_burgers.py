@@ -169,6 +169,7 @@ class GaussianDiffusion(nn.Module):
         # and the batched time tensor from fixed buffers, and replayed every step; the guidance callable (user autograd) and the
         # two fused sampler kernels stay eager.  Same kernels, same arithmetic as the eager loop (tests/test_burgers_sampler.py).
         self.use_cuda_graph = False
+        self.two_streams = True           # graph mode: the two networks of the two-model sampler on two captured streams
         self._net_graph = None
 
     def _sched(self):
@@ -197,9 +198,21 @@ class GaussianDiffusion(nn.Module):
         ti = int(t[0].item()) if torch.is_tensor(t) else int(t)
         return self._predict(x.contiguous(), ti, clip_x_start, **kwargs)[:2]
 
-    def _networks(self, x, tt):
-        """The network forwards of one step (burgers.py:398-417) -> (eps, eps_w or None); mutates x for is_model_w like the reference."""
+    def _networks(self, x, tt, side=None):
+        """The network forwards of one step (burgers.py:398-417) -> (eps, eps_w or None); mutates x for is_model_w like the reference.
+        `side`: a second CUDA stream for the prior network of the two-model sampler (the two forwards are independent and, at 16 KB
+        per trajectory, each leaves most of the GPU idle)."""
         if self.eval_two_models:
+            if side is not None:
+                main = torch.cuda.current_stream(x.device)
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    x_w = x.clone()
+                    x_w[..., 0, 1:self.condition_idx, :] = 0      # burgers.py:400-401
+                    eps_w = self.model_w(x_w, tt)
+                eps_uw = self.model_uw(x, tt)
+                main.wait_stream(side)
+                return eps_uw, eps_w
             eps_uw = self.model_uw(x, tt)
             x_w = x.clone()
             x_w[..., 0, 1:self.condition_idx, :] = 0          # burgers.py:400-401
@@ -210,7 +223,7 @@ class GaussianDiffusion(nn.Module):
 
     def _graphed_networks(self, x, ti):
         models = (self.model_uw, self.model_w) if self.eval_two_models else (self.model,)
-        key = (tuple(x.shape), str(x.device), self.eval_two_models, self.is_model_w, self.condition_idx,
+        key = (tuple(x.shape), str(x.device), self.eval_two_models, self.is_model_w, self.condition_idx, self.two_streams,
                tuple(m._param_key() for m in models), tuple(m.precision for m in models))
         g = self._net_graph
         if g is None or g.key != key:
@@ -359,18 +372,19 @@ class _GraphedNetworks:
         self.x = x.detach().clone()
         self.tt = torch.zeros(x.shape[0], dtype=torch.long, device=dev)
         self.stream = torch.cuda.Stream(device=dev)
+        self.side = torch.cuda.Stream(device=dev) if diff.eval_two_models and diff.two_streams else None
         cur = torch.cuda.current_stream(dev)
         self.stream.wait_stream(cur)
-        with torch.no_grad(), torch.cuda.stream(self.stream):   # warm-up on the capture stream: packs weights, fills the buffer pools
+        with torch.no_grad(), torch.cuda.stream(self.stream):   # warm-up on the capture streams: packs weights, fills the buffer pools
             for _ in range(2):
-                diff._networks(self.x, self.tt)
+                diff._networks(self.x, self.tt, self.side)
         cur.wait_stream(self.stream)
         torch.cuda.synchronize(dev)
         self.x.copy_(x.detach())
         self.graph = torch.cuda.CUDAGraph()
         c0 = _lib.LaunchCounter.count
         with torch.no_grad(), torch.cuda.graph(self.graph, stream=self.stream):
-            self.out = diff._networks(self.x, self.tt)
+            self.out = diff._networks(self.x, self.tt, self.side)
         self.kernels_per_replay = _lib.LaunchCounter.count - c0
 
     def run(self, x, ti):
