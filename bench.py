@@ -316,6 +316,8 @@ def main():
             del warm, bucket
         if args.cuda_graph:                                 # capture (warm-up + one captured step) happens outside the timed region
             diff_k.use_cuda_graph = True
+            if os.environ.get("DPC_TWO_STREAMS"):            # development A/B: force the two U-Nets onto two captured streams (1) or one (0)
+                diff_k.two_streams = os.environ["DPC_TWO_STREAMS"] == "1"
             sample_sharded(diff_k, Bg, design_fn=design_fn, design_guidance="standard", init=init_g, global_noise=True,
                            gather_channels=slice(3, 5))
             launches0 = _lib.LaunchCounter.count

@@ -84,6 +84,7 @@ _SIGNATURES = {
     "dpc_sampler_prepare": ([c_fp] * 3 + [C.c_int32, c_fp, C.c_int32, c_fp, c_fp], C.c_int),
     "dpc_guided_step_dev": ([C.c_int32] + [c_fp] * 9 + [C.c_int32] * 4 + [c_fp], C.c_int),
     "dpc_predict_x_start": ([c_fp, c_fp, C.c_float, C.c_float, C.c_int32, c_fp, C.c_int64, c_fp], C.c_int),
+    "dpc_renoise": ([c_fp, c_fp, C.c_float, C.c_float, c_fp, C.c_int64, c_fp], C.c_int),
     "dpc_burgers_model_output": ([c_fp] * 5 + [C.c_int32] + [C.c_float] * 4 + [C.c_int32, C.c_int64, C.c_int64, c_fp], C.c_int),
     "dpc_ddpm_posterior_step": ([c_fp] * 7 + [C.c_float] * 3 + [C.c_int32] + [C.c_float] * 3 + [C.c_int64, c_fp], C.c_int),
     "dpc_jelly_x_start": ([c_fp] * 3 + [C.c_float] * 2 + [C.c_int32, C.c_int64, C.c_int64, c_fp], C.c_int),
@@ -391,6 +392,12 @@ def sampler_prepare(t_table, c_table, step_index, nsteps, tt, B, cur):
 def guided_step_dev(ddim, x, eps_joint, eps_w, noise, init, coefs_host: StepCoefs, coefs_dev, x_out, x_start_out, B, F, H, W):
     check(lib().dpc_guided_step_dev(1 if ddim else 0, ptr(x), ptr(eps_joint), ptr(eps_w), ptr(noise), ptr(init), C.byref(coefs_host),
                                     ptr(coefs_dev), ptr(x_out), ptr(x_start_out), B, F, H, W, stream_ptr()), "dpc_guided_step_dev")
+    LaunchCounter.count += 1
+
+
+@_timed("renoise")
+def renoise(x, z, a, b, out):
+    check(lib().dpc_renoise(ptr(x), ptr(z), a, b, ptr(out), x.numel(), stream_ptr()), "dpc_renoise")
     LaunchCounter.count += 1
 
 

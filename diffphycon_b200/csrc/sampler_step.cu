@@ -225,6 +225,25 @@ extern "C" int dpc_guided_step_dev(int32_t ddim, const float* x, const float* ep
                                  coefs_dev);
 }
 
+namespace dpc {
+// x_t = a * x + (b * z): the reference's evaluation order (two rounded products, one rounded sum); z may be null (t == 0: + 0)
+__global__ void __launch_bounds__(256) renoise_kernel(const float* x, const float* __restrict__ z, float a, float b, float* out, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = __fadd_rn(__fmul_rn(a, x[i]), z ? __fmul_rn(b, z[i]) : 0.0f);
+}
+}  // namespace dpc
+
+extern "C" int dpc_renoise(const float* x, const float* z, float a, float b, float* out, int64_t n, void* stream) {
+  using namespace dpc;
+  DPC_CHECK_ARG(x && out && n > 0);
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = 148LL * 8 * 4;
+  if (blocks > cap) blocks = cap;
+  renoise_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, z, a, b, out, n);
+  DPC_LAUNCH_CHECK();
+  return 0;
+}
+
 extern "C" int dpc_predict_x_start(const float* x, const float* eps, float sqrt_recip, float sqrt_recipm1, int32_t clip,
                                    float* x_start, int64_t n, void* stream) {
   using namespace dpc;

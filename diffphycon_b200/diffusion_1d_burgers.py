@@ -5,7 +5,8 @@ as burgers.py:line) on the sampling path the reference's inference uses (inferen
 posterior.  Also the guidance helpers callers import from the same module (`get_nablaJ`, the schedulers).
 Network forwards run on the kernels behind `Unet2D`; the elementwise sampler math is two fused kernels per step
 (`dpc_burgers_model_output`, `dpc_ddpm_posterior_step`).  Options the released inference never enables (DDIM,
-residual conditioning, recurrence, 1-D conv models, self-conditioning) raise NotImplementedError."""
+residual conditioning — which the reference's own loop refuses too —, 1-D conv models, self-conditioning) raise NotImplementedError.
+`recurrence` / `recurrence_k` (burgers.py:472-482, :535-578) are implemented."""
 from __future__ import annotations
 
 import math
@@ -95,7 +96,8 @@ class GaussianDiffusion(nn.Module):
         super().__init__()
         if not (temporal and use_conv2d):
             raise NotImplementedError("only the (time, space) 2-D conv models of the released Burgers runs are implemented")
-        if conditioned_on_residual is not None or recurrence or expand_condition or objective != 'pred_noise':
+        if conditioned_on_residual is not None or expand_condition or objective != 'pred_noise':
+            # the reference itself raises NotImplementedError for both residual-conditioning modes inside its loop (burgers.py:552-559)
             raise NotImplementedError("option unused by the released Burgers inference")
         if not eval_two_models:
             self.model = model
@@ -154,7 +156,7 @@ class GaussianDiffusion(nn.Module):
         self.set_unobserved_to_zero_during_sampling = set_unobserved_to_zero_during_sampling
         self.conditioned_on_residual = None
         self.residual_on_u0 = residual_on_u0
-        self.recurrence, self.recurrence_k = False, recurrence_k
+        self.recurrence, self.recurrence_k = bool(recurrence), recurrence_k
         self.is_model_w = is_model_w
         self.eval_two_models = eval_two_models
         self.expand_condition = False
@@ -303,6 +305,19 @@ class GaussianDiffusion(nn.Module):
         pred_noise, x_start, pred = self._predict(x, t, False, clip_denoised=clip, noise=noise, posterior=True, **kw)
         return pred, x_start, pred_noise
 
+    # ---- burgers.py:472-482 ------------------------------------------------------------------------------------
+    @_lib.device_guarded
+    def recurrent_sample(self, x_tm1, t: int):
+        """x_t = sqrt(alpha_t / alpha_{t-1}) x_{t-1} + sqrt(1 - alpha_t / alpha_{t-1}) z (no noise at t == 0); the coefficients are
+        formed in float32 like the reference's extract() tensors."""
+        ratio = self.alphas[t] / self.alphas_prev[t]
+        a, b = float(torch.sqrt(ratio)), float(torch.sqrt(1 - ratio))
+        x_tm1 = x_tm1.contiguous()
+        z = self.sample_noise(x_tm1.shape, x_tm1.device) if t > 0 else None
+        out = torch.empty_like(x_tm1)
+        _lib.renoise(x_tm1, z, a, b, out)
+        return out
+
     def set_condition(self, img, u, shape, u0_or_uT):
         """burgers.py:500-522 (4-D samples, no expand_condition)."""
         assert len(shape) == 4
@@ -326,23 +341,27 @@ class GaussianDiffusion(nn.Module):
             from tqdm.auto import tqdm
             steps = tqdm(steps, desc='sampling loop time step', total=self.num_timesteps)
         for t in steps:
-            if self.is_condition_u0:
-                self.set_condition(img, kwargs['u_init'].to(device), shape, 'u0')
-            if self.is_condition_uT:
-                self.set_condition(img, kwargs['u_final'].to(device), shape, 'uT')
-            if self.set_unobserved_to_zero_during_sampling:
-                Nx = img.size(-1)
-                img[:, 0, :, Nx // 4:(Nx * 3) // 4] = 0
-            img_curr, x_start, pred_noise = self.p_sample(img, t, None, residual=None, **kwargs)
-            if self.guidance_u0:
-                img = img_curr
-            else:
-                gj = nablaJ(img_curr) if nablaJ is not None else 0
-                sc = Js(t) if Js is not None else 1.
-                pn = proj(pred_noise, gj * sc) if proj is not None else pred_noise + gj * sc
-                kw = dict(kwargs)
-                kw['pred_noise'] = pn
-                img, x_start, _ = self.p_sample(img, t, None, residual=None, **kw)
+            for _k in range(self.recurrence_k):              # burgers.py:535: one pass unless `recurrence`
+                if self.is_condition_u0:
+                    self.set_condition(img, kwargs['u_init'].to(device), shape, 'u0')
+                if self.is_condition_uT:
+                    self.set_condition(img, kwargs['u_final'].to(device), shape, 'uT')
+                if self.set_unobserved_to_zero_during_sampling:
+                    Nx = img.size(-1)
+                    img[:, 0, :, Nx // 4:(Nx * 3) // 4] = 0
+                img_curr, x_start, pred_noise = self.p_sample(img, t, None, residual=None, **kwargs)
+                if self.guidance_u0:
+                    img = img_curr
+                else:
+                    gj = nablaJ(img_curr) if nablaJ is not None else 0
+                    sc = Js(t) if Js is not None else 1.
+                    pn = proj(pred_noise, gj * sc) if proj is not None else pred_noise + gj * sc
+                    kw = dict(kwargs)
+                    kw['pred_noise'] = pn
+                    img, x_start, _ = self.p_sample(img, t, None, residual=None, **kw)
+                if not self.recurrence:
+                    break
+                img = self.recurrent_sample(img, t)          # self recurrence: add back the noise (after EVERY pass, like the reference)
         return self.unnormalize(img)
 
     def ddim_sample(self, shape, return_all_timesteps=False, **kwargs):

@@ -241,6 +241,10 @@ int dpc_guided_step_dev(int32_t ddim, const float* x, const float* eps_joint, co
                         const float* init, const dpc_step_coefs* coefs_host, const dpc_step_coefs* coefs_dev, float* x_out,
                         float* x_start_out, int32_t B, int32_t F, int32_t H, int32_t W, void* stream);
 /* x_start = maybe_clip(sqrt_recip*x - sqrt_recipm1*eps) — smoke.py:576-580, :620-621; for user design_fn callables. */
+/* Self-recurrence re-noising of the Burgers sampler — diffusion_1d_burgers.py:472-482 (recurrent_sample):
+ * out = a * x + b * z with a = sqrt(alpha_t / alpha_{t-1}), b = sqrt(1 - alpha_t / alpha_{t-1}) (products and sum rounded like the
+ * reference's tensor ops); z NULL at t == 0 (no noise).  out may alias x. */
+int dpc_renoise(const float* x, const float* z, float a, float b, float* out, int64_t n, void* stream);
 int dpc_predict_x_start(const float* x, const float* eps, float sqrt_recip, float sqrt_recipm1, int32_t clip,
                         float* x_start, int64_t n, void* stream);
 

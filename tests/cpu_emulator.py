@@ -254,6 +254,11 @@ def time_proj(t_emb, W, bias, out, B, tdim, total):
     out[: B * total] = (e @ W.t() + bias).reshape(-1)
 
 
+def renoise(x, z, a, b, out):
+    v = torch.tensor(a, dtype=torch.float32) * x
+    out.copy_(v + (torch.tensor(b, dtype=torch.float32) * z if z is not None else 0.0))
+
+
 def predict_x_start(x, eps, sr, srm1, clip, out):
     v = np.float32(sr) * x - np.float32(srm1) * eps
     out.copy_(v.clamp(-1, 1) if clip else v)
@@ -476,7 +481,7 @@ def time_mlp_bwd(t, freqs, w1, b1, w2, w_proj, t_emb, dss, dt, B, dim, total):
     dt.copy_(g)
 
 
-EMULATED = ("temporal_block_fused", "gn_fold", "gn_stats_merge", "final_proj", "spatial_linear_block_fused", "stem_conv", "jelly_x_start", "jelly_step", "jelly_write_bd", "burgers_model_output", "ddpm_posterior_step", "conv", "groupnorm_silu", "layernorm_channels", "pack_input", "temporal_attention", "spatial_attention",
+EMULATED = ("temporal_block_fused", "gn_fold", "gn_stats_merge", "renoise", "final_proj", "spatial_linear_block_fused", "stem_conv", "jelly_x_start", "jelly_step", "jelly_write_bd", "burgers_model_output", "ddpm_posterior_step", "conv", "groupnorm_silu", "layernorm_channels", "pack_input", "temporal_attention", "spatial_attention",
             "spatial_linear_attention", "time_embed", "time_proj", "predict_x_start", "guided_step", "upsample_nearest2x",
             "spatial_linear_attention_ex", "linattn2d_bwd", "attention2d_bwd", "gn_silu_bwd", "layernorm_channels_bwd", "add", "sumpool2x2",
             "mean_head", "mean_head_bwd", "time_embed_f32", "time_mlp_bwd")

@@ -39,10 +39,13 @@ def run(name, models, guidance_u0, **dkw):
 
     def rec_ps(x, t, *a, **k):
         tag = f"{t}" if "pred_noise" not in k else f"{t}b"
-        trace[f"x{tag}"] = x.detach().clone().numpy()
+        first = f"x{tag}" not in trace                  # with recurrence p_sample runs recurrence_k times per t: keep the first pass
+        if first:
+            trace[f"x{tag}"] = x.detach().clone().numpy()
         out = orig_ps(x, t, *a, **k)
-        trace[f"pred{tag}"] = out[0].detach().clone().numpy()
-        trace[f"xstart{tag}"] = out[1].detach().clone().numpy()
+        if first:
+            trace[f"pred{tag}"] = out[0].detach().clone().numpy()
+            trace[f"xstart{tag}"] = out[1].detach().clone().numpy()
         return out
 
     d.p_sample = rec_ps
@@ -65,6 +68,13 @@ def run(name, models, guidance_u0, **dkw):
 
 
 uw, w = build(KW_UW, 31), build(KW_W, 32)
-run("burgers_sampler", (uw, w), True, eval_two_models=True, prior_beta=1.5)
-run("burgers_sampler_single_ut", uw, False)
-run("burgers_sampler_model_w", w, True, is_model_w=True, prior_beta=0.7)
+VARIANTS = {
+    "burgers_sampler": lambda: run("burgers_sampler", (uw, w), True, eval_two_models=True, prior_beta=1.5),
+    "burgers_sampler_single_ut": lambda: run("burgers_sampler_single_ut", uw, False),
+    "burgers_sampler_model_w": lambda: run("burgers_sampler_model_w", w, True, is_model_w=True, prior_beta=0.7),
+    # self recurrence (burgers.py:472-482, :535-578): two passes per diffusion step, re-noised after each
+    "burgers_sampler_recurrent": lambda: run("burgers_sampler_recurrent", (uw, w), True, eval_two_models=True, prior_beta=1.5,
+                                             recurrence=True, recurrence_k=2),
+}
+for name in (sys.argv[1:] or list(VARIANTS)):
+    VARIANTS[name]()

@@ -30,6 +30,8 @@ VARIANTS = {   # golden name -> (models, guidance_u0, diffusion kwargs), as in m
     "burgers_sampler": ("both", True, dict(eval_two_models=True, prior_beta=1.5)),
     "burgers_sampler_single_ut": ("uw", False, {}),
     "burgers_sampler_model_w": ("w", True, dict(is_model_w=True, prior_beta=0.7)),
+    # self recurrence (burgers.py:472-482, :535-578): two passes per diffusion step, each followed by recurrent_sample
+    "burgers_sampler_recurrent": ("both", True, dict(eval_two_models=True, prior_beta=1.5, recurrence=True, recurrence_k=2)),
 }
 
 
@@ -160,5 +162,5 @@ def test_burgers_cuda_graph_networks_equal_eager(variant, golden_dir):
         n0 = _lib.LaunchCounter.graph_launches
         out.append(d.sample(batch_size=2, clip_denoised=True, guidance_u0=VARIANTS[variant][1], **kw))
         if graph:
-            assert _lib.LaunchCounter.graph_launches - n0 == T
+            assert _lib.LaunchCounter.graph_launches - n0 == T * VARIANTS[variant][2].get("recurrence_k", 1)
     assert torch.equal(out[0], out[1]), (out[0] - out[1]).abs().max().item()
