@@ -16,3 +16,10 @@ for rep in sys.argv[1:]:
         for k in KEYS:
             if k in d:
                 print(f"  {k} = {d[k]} {units[hdr.index(k)]}")
+        try:   # achieved DRAM bandwidth of the launch = (bytes read + written) / duration
+            SC = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
+            val = lambda k: float(d[k].replace(",", "")) * SC[units[hdr.index(k)]]
+            gbs = (val("dram__bytes_read.sum") + val("dram__bytes_write.sum")) / val("gpu__time_duration.sum") / 1e9
+            print(f"  achieved DRAM bandwidth = {gbs:.0f} GB/s")
+        except (KeyError, ValueError, ZeroDivisionError):
+            pass

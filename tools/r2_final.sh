@@ -17,7 +17,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-fi
 python tools/launch_list_summary.py gpurun_out/r2f_launches_bench.csv > gpurun_out/r2f_launches_bench.md; gzip -f gpurun_out/r2f_launches_bench.csv; lap launch-list
 ncu --set full --clock-control none --import-source on -k regex:temporal_block -s 1 -c 1 -o gpurun_out/r2f_full_tblock -f python tools/run_kernels_once.py tblock 8 > gpurun_out/r2f_ncu_tblock.log 2>&1
 python tools/ncu_summary.py gpurun_out/r2f_full_tblock.ncu-rep > gpurun_out/r2f_full_tblock.txt 2>&1; rm -f gpurun_out/r2f_full_tblock.ncu-rep
-ncu --set full --clock-control none -k regex:smoke_rollout -s 1 -c 1 -o gpurun_out/r2f_full_rollout -f python tools/time_rollout.py 16 32 > gpurun_out/r2f_ncu_rollout.log 2>&1
+ncu --set full --clock-control none -k regex:smoke_rollout -s 1 -c 1 -o gpurun_out/r2f_full_rollout -f python tools/time_rollout.py 64 32 > gpurun_out/r2f_ncu_rollout.log 2>&1
+ncu --set full --clock-control none -k regex:"guided_step|final_proj|layernorm_channels|time_proj|sinusoidal" -c 8 -o gpurun_out/r2f_full_stream2 -f python bench.py --scaling weak --no-cuda-graph --no-cpu-baseline --no-e2e --no-rollout --no-roofline --batch 8 --steps 1 --warmup 0 > gpurun_out/r2f_ncu_stream2.log 2>&1
+python tools/ncu_summary.py gpurun_out/r2f_full_stream2.ncu-rep > gpurun_out/r2f_full_stream2.txt 2>&1; rm -f gpurun_out/r2f_full_stream2.ncu-rep
 python tools/ncu_summary.py gpurun_out/r2f_full_rollout.ncu-rep > gpurun_out/r2f_full_rollout.txt 2>&1; rm -f gpurun_out/r2f_full_rollout.ncu-rep; lap ncu-full
 python - <<'PY'
 import json,glob
