@@ -3,6 +3,7 @@
 mkdir -p gpurun_out
 T0=$(date +%s); lap() { echo "[lap] $1 $(( $(date +%s) - T0 )) s"; }
 timeout 1800 python -m pytest tests/ -q -m gpu > gpurun_out/r2f_pytest_gpu.log 2>&1; tail -3 gpurun_out/r2f_pytest_gpu.log; lap pytest
+timeout 600 python __graft_entry__.py smoke 2>&1 | tail -2; lap smoke
 run() { name=$1; shift; timeout 900 python bench.py "$@" > gpurun_out/r2f_bench_$name.json 2> gpurun_out/r2f_bench_$name.err; echo "$name rc=$?"; }
 run default --steps 10 --warmup 3; lap default
 run reference --impl reference --steps 2 --warmup 1; lap reference
