@@ -14,8 +14,9 @@ positionally (jf.py:760 vs :703), so in-model guidance is never enabled from p_s
 eps_w over all four channels (jf.py:800-804) whereas the DDIM path pads it onto the theta channel only (jf.py:728-733);
 `ddim_sample` returns the result of the second-to-last pair (jf.py:913-916 `continue` before `final_result` is refreshed),
 so the last model evaluation does not influence the output and is skipped here.
-Not implemented (raise NotImplementedError): only_vis_pressure (hard-coded 64x64 shapes in the reference), cond_steps == 0
-(repaint conditioning), objectives other than pred_noise, 'recurrence' guidance."""
+cond_steps == 0 (unconditional model): the conditions are re-imposed as noisy conditions after every DDPM step (repaint, jf.py:865-873).
+Not implemented (raise NotImplementedError): only_vis_pressure (hard-coded 64x64 shapes in the reference), objectives other than
+pred_noise, 'recurrence' guidance (the reference's p_sample returns None for it, jf.py:789)."""
 from __future__ import annotations
 
 from collections import namedtuple
@@ -108,8 +109,8 @@ class GaussianDiffusion(nn.Module):
 
     def _sched(self):
         if self._host_sched is None:
-            names = ('betas', 'alphas_cumprod', 'sqrt_recip_alphas_cumprod', 'sqrt_recipm1_alphas_cumprod',
-                     'posterior_log_variance_clipped', 'posterior_mean_coef1', 'posterior_mean_coef2')
+            names = ('betas', 'alphas_cumprod', 'sqrt_alphas_cumprod', 'sqrt_one_minus_alphas_cumprod', 'sqrt_recip_alphas_cumprod',
+                     'sqrt_recipm1_alphas_cumprod', 'posterior_log_variance_clipped', 'posterior_mean_coef1', 'posterior_mean_coef2')
             self._host_sched = {n: getattr(self, n).detach().float().cpu() for n in names}
         return self._host_sched
 
@@ -152,8 +153,6 @@ class GaussianDiffusion(nn.Module):
         b, f, c, h, w = shape
         device = self.betas.device
         assert cond is not None
-        if self.cond_steps <= 0:
-            raise NotImplementedError("cond_steps == 0 (repaint conditioning, jf.py:865-873) is not implemented")
         st = self._State()
         st.state_0 = cond[0].to(device).float().contiguous()
         st.bd_0 = cond[1].to(device).float().contiguous()
@@ -167,10 +166,11 @@ class GaussianDiffusion(nn.Module):
             bd_updater.to(device)
             bd_updater.eval()
         cs = self.cond_steps
-        noise_state[:, :cs] = st.state_0.unsqueeze(1)
-        noise_bd[:, :cs] = st.bd_0.unsqueeze(1)
-        noisy_thetas[:, :cs] = th
-        noisy_thetas[:, -cs:] = th
+        if cs > 0:                                                              # conditional model (jf.py:838-842)
+            noise_state[:, :cs] = st.state_0.unsqueeze(1)
+            noise_bd[:, :cs] = st.bd_0.unsqueeze(1)
+            noisy_thetas[:, :cs] = th
+            noisy_thetas[:, -cs:] = th
         st.x = torch.cat([noise_state, noise_bd, noisy_thetas], dim=2).contiguous()
         st.x_next = torch.empty_like(st.x)
         st.x_w = st.x.clone()
@@ -190,6 +190,33 @@ class GaussianDiffusion(nn.Module):
         pred_bd = pred_bd.detach().float().reshape(b * f, 3, *st.x.shape[-2:]).contiguous()
         _lib.jelly_write_bd(pred_bd, st.bd_0, st.x_next, st.x_w, self.cond_steps)
         st.x, st.x_next = st.x_next, st.x
+
+    def _repaint(self, st, t: int):
+        """cond_steps == 0 (unconditional model, jf.py:865-873): the conditions are re-imposed as NOISY conditions, q_sample(., t)
+        with fresh noise, on frame 0 (state, boundary, theta) and on the last frame (theta).  Same draw order as the reference
+        (state, boundary, theta) and the same two rounded products + rounded sum (dpc_renoise)."""
+        s = self._sched()
+        a, bb = float(s['sqrt_alphas_cumprod'][t]), float(s['sqrt_one_minus_alphas_cumprod'][t])
+        dev = st.x.device
+        b, _, _, h, w = st.x.shape
+
+        def q_sample(x0):
+            x0 = x0.contiguous()
+            z = self.sample_noise(list(x0.shape), dev).contiguous()
+            out = torch.empty_like(x0)
+            _lib.renoise(x0, z, a, bb, out)
+            return out
+
+        s0, b0 = q_sample(st.state_0), q_sample(st.bd_0)
+        th = q_sample(st.thetas_0.reshape(b, 1, 1, 1, 1).expand(-1, 1, 1, h, w))[:, 0, 0]   # [B,H,W]
+        for buf in (st.x, st.x_w):
+            buf[:, 0, 3:6] = b0
+            buf[:, 0, 6] = th
+            buf[:, -1, 6] = th
+        st.x[:, 0, 0:3] = s0
+        tm = th.mean(dim=2).mean(dim=1)                                         # jf.py:875: mean over W, then over H
+        st.theta_mean[:, 0] = tm
+        st.theta_mean[:, -1] = tm
 
     def _eps(self, st, t: int):
         mj, mw = self._models()
@@ -215,6 +242,8 @@ class GaussianDiffusion(nn.Module):
         sigma = float((0.5 * s['posterior_log_variance_clipped'][t]).exp())
         self._finish_step(st, None, eps_w, g, noise, ga, gb, float(s['posterior_mean_coef1'][t]),
                           float(s['posterior_mean_coef2'][t]), sigma, False)
+        if self.cond_steps <= 0:
+            self._repaint(st, t)
 
     @torch.no_grad()
     def p_sample_loop(self, shape, design_fn=None, design_guidance="standard", return_all_timesteps=None, cond=None,

@@ -359,9 +359,10 @@ def jelly_step(x, x_start, eps, eps_w, g, noise, state_0, thetas_0, x_next, x_w,
     theta = pred[:, :, 3].clone()
     dtheta.copy_(theta.mean((-1, -2)) - thetas_0[:, None])
     states = pred[:, :, :3].clone()
-    states[:, :cs] = state_0.unsqueeze(1)
-    theta[:, :cs] = th
-    theta[:, -cs:] = th
+    if cs > 0:                                          # `[:, -0:]` would be the whole tensor
+        states[:, :cs] = state_0.unsqueeze(1)
+        theta[:, :cs] = th
+        theta[:, -cs:] = th
     theta_mean.copy_(theta.mean((-1, -2)))
     x_next[:, :, :3] = states
     x_next[:, :, 6] = theta
@@ -370,8 +371,9 @@ def jelly_step(x, x_start, eps, eps_w, g, noise, state_0, thetas_0, x_next, x_w,
 
 def jelly_write_bd(pred_bd, bd_0, x_next, x_w, cond_steps):
     bd = pred_bd.reshape(x_next.shape[0], x_next.shape[1], 3, *x_next.shape[-2:]).clone()
-    bd[:, :cond_steps] = bd_0.unsqueeze(1)
-    bd[:, -cond_steps:] = bd_0.unsqueeze(1)
+    if cond_steps > 0:
+        bd[:, :cond_steps] = bd_0.unsqueeze(1)
+        bd[:, -cond_steps:] = bd_0.unsqueeze(1)
     x_next[:, :, 3:6] = bd
     x_w[:, :, 3:6] = bd
 

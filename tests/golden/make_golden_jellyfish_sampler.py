@@ -29,9 +29,9 @@ def build(out_dim, seed):
     return net.eval()
 
 
-def run(name, guidance, sampling_timesteps=None, eta=0.0, T=5, design=True, B=B, FR=FR, S=S, store_trace=True):
+def run(name, guidance, sampling_timesteps=None, eta=0.0, T=5, design=True, B=B, FR=FR, S=S, store_trace=True, cond_steps=1):
     mj, mw = build(4, 41), build(1, 42)
-    d = jm.GaussianDiffusion([mj, mw], image_size=S, frames=FR, cond_steps=1, timesteps=T, sampling_timesteps=sampling_timesteps,
+    d = jm.GaussianDiffusion([mj, mw], image_size=S, frames=FR, cond_steps=cond_steps, timesteps=T, sampling_timesteps=sampling_timesteps,
                              loss_type='l2', objective='pred_noise', standard_fixed_ratio=0.05, coeff_ratio_J=0.3,
                              coeff_ratio_w=0.4, eval_2ddpm=True, w_prob_exp=0.7, ddim_sampling_eta=eta, device='cpu')
     g = torch.Generator().manual_seed(9)
@@ -76,6 +76,10 @@ def run(name, guidance, sampling_timesteps=None, eta=0.0, T=5, design=True, B=B,
     print(name, sorted(trace), tuple(states.shape), tuple(theta.shape), float(states.abs().mean()))
 
 
+if len(sys.argv) > 1 and sys.argv[1] == "repaint":
+    # cond_steps == 0: the unconditional model with repaint conditioning (jf.py:865-873); the draws include the q_sample noise
+    run("jelly_ddpm_repaint", "standard-alpha", cond_steps=0)
+    sys.exit(0)
 run("jelly_ddpm_alpha", "standard-alpha")
 run("jelly_ddpm_standard", "standard")
 run("jelly_ddpm_noguide", "standard", design=False)

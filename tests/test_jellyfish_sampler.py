@@ -30,8 +30,8 @@ def build(out_dim, seed, precision):
     return net
 
 
-def make(device, precision, S, FR, T, sampling_timesteps=None, eta=0.0):
-    d = dj.GaussianDiffusion([build(4, 41, precision), build(1, 42, precision)], image_size=S, frames=FR, cond_steps=1,
+def make(device, precision, S, FR, T, sampling_timesteps=None, eta=0.0, cond_steps=1):
+    d = dj.GaussianDiffusion([build(4, 41, precision), build(1, 42, precision)], image_size=S, frames=FR, cond_steps=cond_steps,
                              timesteps=T, sampling_timesteps=sampling_timesteps, loss_type='l2', objective='pred_noise',
                              standard_fixed_ratio=0.05, coeff_ratio_J=0.3, coeff_ratio_w=0.4, eval_2ddpm=True, w_prob_exp=0.7,
                              ddim_sampling_eta=eta, device='cpu')
@@ -67,9 +67,9 @@ def check_ddpm_steps(z, name, device, precision, tol):
             assert (st.theta_mean.cpu() - ref_t).abs().max().item() <= tol * amp
 
 
-def check_ddpm_loop(z, name, device):
-    guidance, design = DDPM[name]
-    d = make(device, "3xtf32", 16, 4, 5)
+def check_ddpm_loop(z, name, device, cond_steps=1):
+    guidance, design = DDPM.get(name, ("standard-alpha", True))
+    d = make(device, "3xtf32", 16, 4, 5, cond_steps=cond_steps)
     nz = len([k for k in z.files if k.startswith("z")])
     it = iter([torch.from_numpy(z[f"z{i}"]).to(device) for i in range(nz)])
     d.sample_noise = lambda shape, dv: next(it)
@@ -114,6 +114,13 @@ def test_jellyfish_ddpm_host_logic_loop(golden_dir, monkeypatch):
     check_ddpm_loop(np.load(os.path.join(golden_dir, "jelly_ddpm_alpha.npz")), "jelly_ddpm_alpha", "cpu")
 
 
+def test_jellyfish_repaint_host_logic_loop(golden_dir, monkeypatch):
+    """cond_steps == 0: unconditional model + repaint conditioning (jf.py:865-873), whole loop against the reference trace (the
+    recorded draws include the q_sample noise of the three re-imposed conditions, in the reference's order)."""
+    _emulate(monkeypatch)
+    check_ddpm_loop(np.load(os.path.join(golden_dir, "jelly_ddpm_repaint.npz")), "jelly_ddpm_repaint", "cpu", cond_steps=0)
+
+
 def test_jellyfish_ddim_host_logic(golden_dir, monkeypatch):
     _emulate(monkeypatch)
     check_ddim(np.load(os.path.join(golden_dir, "jelly_ddim_alpha.npz")), "jelly_ddim_alpha", "cpu", "3xtf32", 2e-4)
@@ -123,9 +130,9 @@ def test_unimplemented_options_raise():
     net = Unet3D_with_Conv3D(dim=32, dim_mults=(1, 2), channels=7, out_dim=4)
     with pytest.raises(NotImplementedError):
         dj.GaussianDiffusion(net, image_size=16, only_vis_pressure=True)
-    d = dj.GaussianDiffusion([net, net], image_size=16, frames=4, cond_steps=0, timesteps=4, eval_2ddpm=True)
-    with pytest.raises(NotImplementedError):
-        d.sample(cond=[torch.zeros(1, 3, 16, 16), torch.zeros(1, 3, 16, 16)], thetas_0=torch.zeros(1), bd_updater=bd_updater)
+    d = dj.GaussianDiffusion([net, net], image_size=16, frames=4, cond_steps=1, timesteps=4, eval_2ddpm=True)
+    with pytest.raises(NotImplementedError):       # the reference's p_sample returns None for it (jf.py:789)
+        d._ddpm_step(None, 0, None, "recurrence")
 
 
 @pytest.mark.gpu
@@ -139,6 +146,11 @@ def test_jellyfish_ddpm_steps_gpu(name, precision, tol, golden_dir):
 @pytest.mark.parametrize("name", list(DDPM))
 def test_jellyfish_ddpm_loop_gpu(name, golden_dir):
     check_ddpm_loop(np.load(os.path.join(golden_dir, name + ".npz")), name, "cuda")
+
+
+@pytest.mark.gpu
+def test_jellyfish_repaint_loop_gpu(golden_dir):
+    check_ddpm_loop(np.load(os.path.join(golden_dir, "jelly_ddpm_repaint.npz")), "jelly_ddpm_repaint", "cuda", cond_steps=0)
 
 
 @pytest.mark.gpu
