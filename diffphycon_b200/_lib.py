@@ -288,9 +288,11 @@ def pack_input(x, out, B, F, Ctot, c0, Cin, H, W, Cpad):
 
 
 @_timed("temporal_attention")
-def temporal_attention(qkv, rope_cos, rope_sin, pos_bias, out, B, F, HW, heads, use_rope=True, precise=False):
+def temporal_attention(qkv, rope_cos, rope_sin, pos_bias, out, B, F, HW, heads, use_rope=True, precise=False, relative_bias=False):
+    """relative_bias: pos_bias[h][i][j] is a function of j - i only (RelativePositionBias): read through a shared-memory table."""
     check(lib().dpc_temporal_attention(ptr(qkv), ptr(rope_cos), ptr(rope_sin), ptr(pos_bias), ptr(out), B, F, HW, heads,
-                                       1 if use_rope else 0, 1 if precise else 0, stream_ptr()), "dpc_temporal_attention")
+                                       (1 if use_rope else 0) | (2 if relative_bias else 0), 1 if precise else 0, stream_ptr()),
+          "dpc_temporal_attention")
     LaunchCounter.count += 1
 
 

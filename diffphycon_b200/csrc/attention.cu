@@ -68,6 +68,20 @@ temporal_attention_mma_kernel(const float* __restrict__ qkv, const float* __rest
   const int C3 = 3 * heads * DH, hid = heads * DH;
   const int g = lane >> 2, t = lane & 3;
   const int lf = lane >> 3, lc = (lane & 7) * 4;      // staging: frame-in-group, first channel of this lane's float4
+  // flags bit 1: pos_bias[h][i][j] depends on j - i only (RelativePositionBias, conv3d.py:110-148): one [heads][2 NF] table in
+  // shared memory instead of global loads that touch 8 cache lines per warp instruction
+  const bool rel = pos_bias && (use_rope & 2);
+  float* bias_s = sm + (size_t)4 * 3 * NF * LD;
+  if (rel) {
+    for (int i = threadIdx.x; i < heads * 2 * NF; i += 128) {
+      const int h = i / (2 * NF), d = i - h * 2 * NF - (NF - 1);
+      float v = 0.f;
+      if (d < F && -d < F) v = (d >= 0) ? __ldg(pos_bias + ((size_t)h * F + 0) * F + d) : __ldg(pos_bias + ((size_t)h * F - d) * F + 0);
+      bias_s[i] = v;
+    }
+    __syncthreads();
+  }
+  use_rope &= 1;
 
   for (int64_t wg = (int64_t)blockIdx.x * 4 + warp; wg < total_warps; wg += (int64_t)gridDim.x * 4) {
     const int head = (int)(wg % heads);
@@ -142,7 +156,8 @@ temporal_attention_mma_kernel(const float* __restrict__ qkv, const float* __rest
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int row = qh * 32 + mt * 16 + g + 8 * h;
-          const float* brow = (pos_bias && row < F) ? pos_bias + ((size_t)head * F + row) * F : nullptr;
+          const float* brow = (!rel && pos_bias && row < F) ? pos_bias + ((size_t)head * F + row) * F : nullptr;
+          const float* brel = bias_s + head * 2 * NF + (NF - 1) - row;
           float mx = -INFINITY;
 #pragma unroll
           for (int nt = 0; nt < NKT; ++nt)
@@ -150,7 +165,8 @@ temporal_attention_mma_kernel(const float* __restrict__ qkv, const float* __rest
             for (int e = 0; e < 2; ++e) {
               const int col = nt * 8 + 2 * t + e;
               float v = s[mt][nt][2 * h + e];
-              if (brow && col < F) v += __ldg(brow + col);
+              if (rel) v += brel[col];
+              else if (brow && col < F) v += __ldg(brow + col);
               if (col >= F) v = -INFINITY;
               s[mt][nt][2 * h + e] = v;
               mx = fmaxf(mx, v);
@@ -162,7 +178,7 @@ temporal_attention_mma_kernel(const float* __restrict__ qkv, const float* __rest
           for (int nt = 0; nt < NKT; ++nt)
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
-              const float pv = expf(s[mt][nt][2 * h + e] - mx);
+              const float pv = PRECISE ? expf(s[mt][nt][2 * h + e] - mx) : __expf(s[mt][nt][2 * h + e] - mx);
               s[mt][nt][2 * h + e] = pv;
               l += pv;
             }
@@ -618,7 +634,7 @@ extern "C" int dpc_temporal_attention(const float* qkv, const float* rope_cos, c
                                       int32_t heads, int32_t use_rope, int32_t precise, void* stream) {
   using namespace dpc;
   DPC_CHECK_ARG(qkv && out && B > 0 && F > 0 && F <= 64 && HW > 0 && heads > 0);
-  DPC_CHECK_ARG(!use_rope || (rope_cos && rope_sin));
+  DPC_CHECK_ARG(!(use_rope & 1) || (rope_cos && rope_sin));
   const int64_t total = (int64_t)B * HW * heads;
   int64_t blocks = (total + 3) / 4;
   const int64_t cap = 148LL * 64;
@@ -626,11 +642,12 @@ extern "C" int dpc_temporal_attention(const float* qkv, const float* rope_cos, c
   cudaStream_t st = (cudaStream_t)stream;
   // F <= 32 and 32 < F <= 64 both run the tensor-core kernel (frames padded to 32 / 64, padded keys masked)
   const int NFr = F <= 32 ? 32 : 64;
-  const size_t smem = (size_t)4 * 3 * NFr * 36 * sizeof(float);
+  DPC_CHECK_ARG(heads <= 16);
+  const size_t smem = ((size_t)4 * 3 * NFr * 36 + (size_t)heads * 2 * NFr) * sizeof(float);
   static bool configured_[kMaxDevices] = {};
   bool& configured = configured_[device_ordinal()];
   if (!configured) {
-    const int s32 = 4 * 3 * 32 * 36 * (int)sizeof(float), s64 = 4 * 3 * 64 * 36 * (int)sizeof(float);
+    const int s32 = (4 * 3 * 32 * 36 + 16 * 64) * (int)sizeof(float), s64 = (4 * 3 * 64 * 36 + 16 * 128) * (int)sizeof(float);
     DPC_CUDA(cudaFuncSetAttribute(temporal_attention_mma_kernel<false, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, s32));
     DPC_CUDA(cudaFuncSetAttribute(temporal_attention_mma_kernel<true, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, s32));
     DPC_CUDA(cudaFuncSetAttribute(temporal_attention_mma_kernel<false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, s64));

@@ -637,7 +637,8 @@ class Unet3D_with_Conv3D(nn.Module):
             pool.put(xn)
             att = pool.get(m * hid)
             if kind == "temporal":
-                _lib.temporal_attention(qkv, G["rope.cos"], G["rope.sin"], G["pos_bias"], att, B, F, h * w, heads, True, precise)
+                _lib.temporal_attention(qkv, G["rope.cos"], G["rope.sin"], G["pos_bias"], att, B, F, h * w, heads, True, precise,
+                                        relative_bias=True)
             elif kind == "spatial":
                 _lib.spatial_attention(qkv, att, B * F, h * w, heads, precise=precise)
             else:

@@ -140,7 +140,8 @@ int dpc_pack_input(const float* x, float* out, int32_t B, int32_t F, int32_t Cto
  * ------------------------------------------------------------------------------------------------------- */
 /* Temporal softmax attention over frames per pixel with RoPE on q,k and T5 relative bias — conv3d.py:293-352,
  * rotary-embedding-torch 0.8.4 rotate_queries_or_keys.  rope_cos/rope_sin: [F][32] (angle table, interleaved pairs);
- * pos_bias: [heads][F][F] or NULL; use_rope 0 skips the rotation. F <= 64.  The two contractions run on tensor cores
+ * pos_bias: [heads][F][F] or NULL; use_rope bit 0: rotate q,k (0 skips the rotation); bit 1: pos_bias[h][i][j] depends on j - i only
+ * (RelativePositionBias, conv3d.py:110-148) and is read through a [heads][2F-1] shared-memory table. F <= 64.  The two contractions run on tensor cores
  * (mma.sync m16n8k8; precise 0: TF32 operands, 1: 3xTF32 split products, fp32-class like the reference's einsum); frames are
  * padded to 32 (F <= 32) or 64 (32 < F <= 64) with the padded keys masked out. */
 int dpc_temporal_attention(const float* qkv, const float* rope_cos, const float* rope_sin, const float* pos_bias,

@@ -149,7 +149,7 @@ def _split_heads(qkv, heads):
     return f(q), f(k), f(v)
 
 
-def temporal_attention(qkv, rope_cos, rope_sin, pos_bias, out, B, F, HW, heads, use_rope=True, precise=False):
+def temporal_attention(qkv, rope_cos, rope_sin, pos_bias, out, B, F, HW, heads, use_rope=True, precise=False, relative_bias=False):
     hid = heads * HEADS_DIM
     t = qkv[: B * F * HW * 3 * hid].reshape(B, F, HW, 3 * hid).permute(0, 2, 1, 3)  # b hw f c
     q, k, v = _split_heads(t, heads)

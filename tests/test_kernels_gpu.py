@@ -306,6 +306,15 @@ def test_temporal_attention(Fr, precise):
     _lib.temporal_attention(qkv.to(DEV), None, None, None, out2, B, Fr, HW, heads, False, precise)
     emu.temporal_attention(qkv.reshape(-1).double(), None, None, None, ref, B, Fr, HW, heads, False)
     assert rel_err(out2.reshape(-1), ref) <= tol
+    # a relative bias (function of j - i, like RelativePositionBias) through the shared-memory table: same result as the general form
+    tab = torch.randn(heads, 2 * Fr - 1, generator=gen)
+    idx = torch.arange(Fr)[None, :] - torch.arange(Fr)[:, None] + Fr - 1
+    rbias = tab[:, idx].contiguous()
+    out3, out4 = torch.empty_like(out), torch.empty_like(out)
+    _lib.temporal_attention(qkv.to(DEV), ang.cos().to(DEV), ang.sin().to(DEV), rbias.to(DEV), out3, B, Fr, HW, heads, True, precise,
+                            relative_bias=True)
+    _lib.temporal_attention(qkv.to(DEV), ang.cos().to(DEV), ang.sin().to(DEV), rbias.to(DEV), out4, B, Fr, HW, heads, True, precise)
+    assert torch.equal(out3, out4)
 
 
 @pytest.mark.parametrize("HW", [16, 100, 256])
