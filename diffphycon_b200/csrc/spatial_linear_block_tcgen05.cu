@@ -502,6 +502,208 @@ linattn_apply_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_co
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------------------------------
+// 3b. apply pass, software-pipelined (default): same arithmetic as linattn_apply_tc_kernel, but the two tensor-core steps of a
+// tile no longer leave the row threads idle.  The accumulators are double-buffered in TMEM (2 x [q 128 | y 64 | raw x 64] = 512
+// columns), the x tile ring has three slots (a slot doubles as the store staging of its tile, so the load of tile i+3 waits for
+// the store of tile i) and the frame's folded out-projection MT has its own two-slot ring.  Row threads per tile:
+//   softmax(i)  |  LayerNorm(i+1) while the y MMA(i) runs  |  epilogue(i) while the q MMA(i+1) runs
+// ------------------------------------------------------------------------------------------------------------------------
+constexpr uint32_t P_OFF_W = 0;                           // 2 chunks x [128 rows x 128 B] (to_q)
+constexpr uint32_t P_OFF_XA = 32768;                      // 3 slots x XA_BYTES
+constexpr uint32_t P_OFF_MT = P_OFF_XA + 3 * XA_BYTES;    // 2 slots x 4 (h,d) chunks x [64 rows x 128 B]
+constexpr uint32_t P_OFF_BIAS = P_OFF_MT + 2 * MT_BYTES;  // float [64]
+constexpr uint32_t P_OFF_EXLN = P_OFF_BIAS + 256;
+constexpr uint32_t P_OFF_BAR = P_OFF_EXLN + 2048;
+constexpr uint32_t P_SMEM = P_OFF_BAR + 128 + 1024;
+
+__global__ void __launch_bounds__(THREADS, 1)
+linattn_apply_pipe_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
+                          const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmM, const ApplyParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  float* bias_s = reinterpret_cast<float*>(gbase + P_OFF_BIAS);
+  const uint32_t bars = base + P_OFF_BAR;
+  const uint32_t w_full = bars, x_full = bars + 8, x_empty = bars + 32, mt_full = bars + 56, mt_empty = bars + 72;
+  const uint32_t a_ready = bars + 88, q_full = bars + 96, qs_ready = bars + 104, y_full = bars + 112, tmem_slot = bars + 120;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nloc = ((int)blockIdx.x < p.ntiles) ? (p.ntiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+
+  if (threadIdx.x == 0) {
+    mbar_init(w_full, 1);
+    for (int i = 0; i < 3; ++i) { mbar_init(x_full + 8 * i, 1); mbar_init(x_empty + 8 * i, 8); }
+    for (int i = 0; i < 2; ++i) { mbar_init(mt_full + 8 * i, 1); mbar_init(mt_empty + 8 * i, 1); }
+    mbar_init(a_ready, 256);
+    mbar_init(q_full, 1);
+    mbar_init(qs_ready, 256);
+    mbar_init(y_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmX) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmY) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmM) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (threadIdx.x < C) bias_s[threadIdx.x] = p.bias ? __ldg(p.bias + threadIdx.x) : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0 && lane == 0) {
+    // ------------------------------------------- TMA producer -------------------------------------------
+    if (nloc > 0) {
+      mbar_expect_tx(w_full, 32768);
+      for (int c = 0; c < 2; ++c) tma_load_2d(base + P_OFF_W + c * 16384, &tmW, w_full, c * 32, 0);
+    }
+    for (int i = 0; i < nloc; ++i) {
+      const int tile = blockIdx.x + i * gridDim.x;
+      const int xs = i % 3, ms = i & 1;
+      mbar_wait(x_empty + 8 * xs, ((i / 3) & 1) ^ 1);
+      mbar_expect_tx(x_full + 8 * xs, XA_BYTES);
+      const uint32_t dst = base + P_OFF_XA + xs * XA_BYTES;
+      for (int c = 0; c < 2; ++c) tma_load_2d(dst + c * 16384, &tmX, x_full + 8 * xs, c * 32, tile * TP);
+      mbar_wait(mt_empty + 8 * ms, ((i >> 1) & 1) ^ 1);
+      mbar_expect_tx(mt_full + 8 * ms, MT_BYTES);
+      const uint32_t dm = base + P_OFF_MT + ms * MT_BYTES;
+      const int frame = tile / p.tpf;
+      for (int kc = 0; kc < 4; ++kc) tma_load_2d(dm + kc * 8192, &tmM, mt_full + 8 * ms, kc * 32, frame * C);
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------- MMA issuer ---------------------------------------------
+    const uint64_t w_desc = umma_desc(base + P_OFF_W);
+    auto issue_q = [&](int i) {
+      const uint64_t xa_desc = umma_desc(base + P_OFF_XA + (i % 3) * XA_BYTES);
+      const uint32_t tq = tmem_base + 256u * (uint32_t)(i & 1);
+      mbar_wait(a_ready, i & 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_tf32(tq, xa_desc + (uint64_t)(c * (16384 >> 4) + 2 * k), w_desc + (uint64_t)(c * (16384 >> 4) + 2 * k), IDESC_N128,
+                      (uint32_t)(c | k));
+        umma_commit(q_full);
+      }
+      __syncwarp();
+    };
+    if (nloc > 0) {
+      mbar_wait(w_full, 0);
+      issue_q(0);
+    }
+    for (int i = 0; i < nloc; ++i) {
+      const uint32_t ts = tmem_base + 256u * (uint32_t)(i & 1);
+      const uint64_t mt_desc = umma_desc(base + P_OFF_MT + (i & 1) * MT_BYTES);
+      mbar_wait(qs_ready, i & 1);
+      mbar_wait(mt_full + 8 * (i & 1), (i >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_tf32_ts(ts + 128, ts + (uint32_t)(kc * 32 + k * 8), mt_desc + (uint64_t)(kc * (8192 >> 4) + 2 * k), IDESC_N64,
+                         (uint32_t)(kc | k));
+        umma_commit(y_full);
+        umma_commit(mt_empty + 8 * (i & 1));
+      }
+      __syncwarp();
+      if (i + 1 < nloc) issue_q(i + 1);
+    }
+  } else if (warp >= 4 && nloc > 0) {
+    // ------------------------------------------- row threads --------------------------------------------
+    const int q = warp & 3;
+    const int gi = (warp - 4) >> 2;                      // channel chunk gi (LayerNorm, output), heads 2gi and 2gi+1 (softmax)
+    const int r = q * 32 + lane;                         // pixel of the tile == TMEM lane
+    const uint32_t sw = (uint32_t)(lane & 7);
+    const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16);
+    float2* exln = reinterpret_cast<float2*>(gbase + P_OFF_EXLN);
+    auto layernorm = [&](int i) {                        // LayerNorm of local tile i in place, raw x parked in its TMEM set
+      const int xs = i % 3;
+      mbar_wait(x_full + 8 * xs, (i / 3) & 1);
+      layernorm_row<true>(base + P_OFF_XA + xs * XA_BYTES, gi, r, sw, exln, p.eps, tlane + 256u * (uint32_t)(i & 1) + 192 + gi * 32);
+      fence_async_proxy();
+      tc_fence_before();
+      mbar_arrive(a_ready);
+    };
+    layernorm(0);
+    for (int i = 0; i < nloc; ++i) {
+      const int tile = blockIdx.x + i * gridDim.x;
+      const uint32_t ts = tlane + 256u * (uint32_t)(i & 1);
+      const uint32_t mine = base + P_OFF_XA + (uint32_t)((i % 3) * XA_BYTES) + (uint32_t)((gi * 4 + q) * 4096);   // rows of chunk gi; later the output box
+      // ---- q~ = softmax over d per head, in place in TMEM (the A operand of the second MMA) ----
+      mbar_wait(q_full, i & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        uint32_t v[32];
+        const uint32_t col = ts + (uint32_t)((2 * gi + hh) * DH);
+        tmem_ld32(col, v);
+        tmem_wait_ld();
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float e0 = __expf(__uint_as_float(v[j]) - mx), e1 = __expf(__uint_as_float(v[j + 1]) - mx);
+          v[j] = __float_as_uint(e0);
+          v[j + 1] = __float_as_uint(e1);
+          s0 += e0;
+          s1 += e1;
+        }
+        const float inv = 1.0f / (s0 + s1);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = to_tf32(__uint_as_float(v[j]) * inv);
+        tmem_st32(col, v);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(qs_ready);
+      // ---- the previous tile's TMA store has finished reading its slot: hand it back to the producer ----
+      if (i > 0 && lane == 0) {
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        mbar_arrive(x_empty + 8 * ((i - 1) % 3));
+      }
+      __syncwarp();
+      // ---- LayerNorm of the next tile while the tensor core multiplies this one ----
+      if (i + 1 < nloc) layernorm(i + 1);
+      // ---- y + bias + raw x -> swizzled box (in this tile's x slot) -> TMA store ----
+      mbar_wait(y_full, i & 1);
+      tc_fence_after();
+      {
+        uint32_t yv[32], xv[32];
+        tmem_ld32(ts + 128 + gi * 32, yv);
+        tmem_ld32(ts + 192 + gi * 32, xv);
+        tmem_wait_ld();
+        const float* bs = bias_s + gi * 32;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          sts128(mine + lane * 128 + ((j ^ sw) << 4), __uint_as_float(yv[4 * j]) + bs[4 * j] + __uint_as_float(xv[4 * j]),
+                 __uint_as_float(yv[4 * j + 1]) + bs[4 * j + 1] + __uint_as_float(xv[4 * j + 1]),
+                 __uint_as_float(yv[4 * j + 2]) + bs[4 * j + 2] + __uint_as_float(xv[4 * j + 2]),
+                 __uint_as_float(yv[4 * j + 3]) + bs[4 * j + 3] + __uint_as_float(xv[4 * j + 3]));
+      }
+      fence_async_proxy();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tmY, mine, gi * 32, tile * TP + q * 32);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+}
+
 static int make_map_2d(CUtensorMap* m, const float* ptr, int64_t cols, int64_t rows, int box_cols, int box_rows) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return set_err(-1, "cuTensorMapEncodeTiled unavailable", __FILE__, __LINE__);
@@ -544,6 +746,7 @@ extern "C" int dpc_spatial_linear_block_fused(const float* x, const float* w_qkv
   if (!configured) {
     DPC_CUDA(cudaFuncSetAttribute(linattn_context_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM));
     DPC_CUDA(cudaFuncSetAttribute(linattn_apply_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)B_SMEM));
+    DPC_CUDA(cudaFuncSetAttribute(linattn_apply_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P_SMEM));
     configured = true;
   }
   const int num_sms = sm_count(dev);
@@ -554,7 +757,11 @@ extern "C" int dpc_spatial_linear_block_fused(const float* x, const float* w_qkv
   DPC_LAUNCH_CHECK();
   const int tpf = HW / TP, ntiles = BF * tpf;
   ApplyParams pb{b_out, eps, ntiles, tpf};
-  linattn_apply_tc_kernel<<<(unsigned)(ntiles < num_sms ? ntiles : num_sms), THREADS, B_SMEM, st>>>(mx, my, mwq, mm, pb);
+  static const int pipe = getenv("DPC_SL_PIPE") ? atoi(getenv("DPC_SL_PIPE")) : 1;   // 0: the unpipelined apply pass (A/B)
+  if (pipe)
+    linattn_apply_pipe_kernel<<<(unsigned)(ntiles < num_sms ? ntiles : num_sms), THREADS, P_SMEM, st>>>(mx, my, mwq, mm, pb);
+  else
+    linattn_apply_tc_kernel<<<(unsigned)(ntiles < num_sms ? ntiles : num_sms), THREADS, B_SMEM, st>>>(mx, my, mwq, mm, pb);
   DPC_LAUNCH_CHECK();
   return 0;
 }
