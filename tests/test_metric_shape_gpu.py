@@ -168,3 +168,25 @@ def test_ddpm_loop_teacher_forced_tf32(golden_dir):
         rows[f"t{t}"] = dict(err=err, bound=TOL_TF32 * eps_scale * amp + 1e-5, amp=amp, eps_scale=eps_scale)
         assert err <= TOL_TF32 * eps_scale * amp + 1e-5, (t, err, amp)
     report("ddpm4_teacher_forced_tf32", rows)
+
+
+def test_graph_replay_equals_eager_at_metric_shape():
+    """The benchmark replays one captured CUDA graph per denoising step (bench.py strong mode).  At the benchmarked architecture and
+    shape (dim 64, (1,2,4), 32 frames of 64x64, tcgen05 kernels, fused attention blocks) the graph loop must reproduce the eager
+    loop bit for bit on the same seed: same kernels, same arithmetic, same noise stream."""
+    from diffphycon_b200 import _lib
+    torch.manual_seed(0)
+    mj = dpc.Unet3D_with_Conv3D(dim=64, dim_mults=(1, 2, 4), channels=6)
+    mw = dpc.Unet3D_with_Conv3D(dim=64, dim_mults=(1, 2, 4), channels=2)
+    d = dpc.GaussianDiffusion([mj, mw], image_size=64, frames=32, timesteps=3, sampling_timesteps=3, eval_2ddpm=True,
+                              standard_fixed_ratio=1e5, coeff_ratio=0, w_prob_exp=0.97).cuda()
+    init = torch.rand(2, 64, 64, generator=torch.Generator().manual_seed(5)).cuda() / 2
+    fn = dpc.StockSmokeGuidance()
+    torch.manual_seed(11)
+    ref = d.sample(batch_size=2, design_fn=fn, init=init)
+    d.use_cuda_graph = True
+    n0 = _lib.LaunchCounter.graph_launches
+    torch.manual_seed(11)
+    y = d.sample(batch_size=2, design_fn=fn, init=init)
+    assert _lib.LaunchCounter.graph_launches - n0 == 3
+    assert torch.isfinite(y).all() and torch.equal(y, ref), (y - ref).abs().max().item()
